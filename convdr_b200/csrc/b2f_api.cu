@@ -1,0 +1,892 @@
+// b2f_api.cu — host side of the engine behind the C ABI declared in include/b2f.h.
+//
+// One b2f_index owns one shard per device: the fp32 rows (for exact rescoring and the SIMT
+// engine), their bf16 shadow (streamed by the tensor engine), the norm bound of the shard, and a
+// per-shard workspace.  A search is a fixed sequence of kernels per query pass:
+//
+//   prep_queries -> margin -> [score(dense) -> refresh] -> { score(filter) -> refresh }* -> final
+//
+// where "score" is either umma_score_select_kernel (tcgen05) or scan_kernel (SIMT).  There is no
+// CPU arithmetic anywhere on this path; without a CUDA device every entry point fails.
+#include "../../include/b2f.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_scan.cuh"
+#include "kernels_select.cuh"
+#include "kernels_umma.cuh"
+#include "kernels_util.cuh"
+
+using namespace b2f;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(call)                                                                           \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      (void)cudaGetLastError();                                                                \
+      return fail(e_ == cudaErrorMemoryAllocation ? B2F_ERR_OOM : B2F_ERR_CUDA,                \
+                  std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +     \
+                      std::to_string(__LINE__) + ")");                                         \
+    }                                                                                          \
+  } while (0)
+
+#define B2F_TRY(call)        \
+  do {                       \
+    int rc_ = (call);        \
+    if (rc_ != B2F_OK) return rc_; \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, 768] tensor, box = 64 columns (128 bytes) x box_rows, 128-byte swizzle.
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(B2F_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kD), rows};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(kD) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2F_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return B2F_OK;
+}
+
+struct Workspace {
+  // candidate state of one pass
+  int qp_cap = 0, C = 0;
+  uint64_t* cand[2] = {nullptr, nullptr};
+  int* cnt = nullptr;
+  float* tau = nullptr;
+  uint64_t* tauP = nullptr;
+  int* ovf = nullptr;
+  float* margin = nullptr;
+  int* err = nullptr;
+  // queries of one search
+  int64_t nq_cap = 0;
+  float* q32 = nullptr;
+  __nv_bfloat16* q16 = nullptr;
+  float* qnorm = nullptr;
+  int* ovf_all = nullptr;
+  int* ovf_host = nullptr;  // pinned
+  // per-shard results of one search
+  int64_t out_cap = 0;
+  float* D = nullptr;
+  int64_t* I = nullptr;
+  // merge staging (shard 0 only)
+  int64_t parts_cap = 0;
+  float* Dp = nullptr;
+  int64_t* Ip = nullptr;
+  // fallback staging
+  float* fbq = nullptr;   // [kScanMaxQ, 768]
+  float* fbD = nullptr;   // [kScanMaxQ, B2F_MAX_K]
+  int64_t* fbI = nullptr;
+  // pinned host staging for query upload / result download
+  size_t pin_bytes = 0;
+  void* pin = nullptr;
+};
+
+struct Shard {
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev = nullptr;
+  int sm_count = 148;
+  int max_pairs = 74;
+  float* x32 = nullptr;
+  __nv_bfloat16* x16 = nullptr;
+  int64_t n = 0, cap = 0;
+  unsigned int* maxnorm2 = nullptr;  // device, float bits
+  int64_t* idmap = nullptr;          // optional explicit labels [cap]
+  bool has_ids = false;
+  std::vector<Seg> segs;
+  Seg* segs_d = nullptr;
+  int segs_d_cap = 0;
+  Workspace ws;
+};
+
+struct Stats {
+  double launches = 0, phases = 0, candidates = 0, fallback_queries = 0, path = 0, passes = 0;
+};
+
+}  // namespace
+
+struct b2f_index {
+  int d = kD;
+  std::vector<Shard> shards;
+  int64_t ntotal = 0;
+  // options
+  int path = B2F_PATH_AUTO;
+  int shadow = 1;
+  int growth = 16;
+  int64_t margin_ppm = 1000000;
+  int keep_on_reset = 1;
+  int scan_max_auto = 4;  // AUTO: batches up to this size use the SIMT scan
+  Stats stats;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) return B2F_OK;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(B2F_ERR_OOM, "cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes failed: " +
+                                 cudaGetErrorString(e));
+  }
+  return B2F_OK;
+}
+template <typename T>
+void dev_free(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+int ensure_capacity(b2f_index* idx, Shard& S, int64_t need) {
+  if (need <= S.cap) return B2F_OK;
+  CU_TRY(cudaSetDevice(S.dev));
+  int64_t ncap = std::max<int64_t>(need, S.cap + S.cap / 2);
+  float* n32 = nullptr;
+  __nv_bfloat16* n16 = nullptr;
+  int64_t* nid = nullptr;
+  B2F_TRY(dev_alloc(&n32, static_cast<size_t>(ncap) * kD));
+  if (idx->shadow) {
+    int rc = dev_alloc(&n16, static_cast<size_t>(ncap) * kD);
+    if (rc != B2F_OK) { dev_free(n32); return rc; }
+  }
+  if (S.has_ids) {
+    int rc = dev_alloc(&nid, static_cast<size_t>(ncap));
+    if (rc != B2F_OK) { dev_free(n32); dev_free(n16); return rc; }
+  }
+  if (S.n > 0) {
+    CU_TRY(cudaMemcpyAsync(n32, S.x32, static_cast<size_t>(S.n) * kD * 4, cudaMemcpyDeviceToDevice, S.stream));
+    if (n16 && S.x16)
+      CU_TRY(cudaMemcpyAsync(n16, S.x16, static_cast<size_t>(S.n) * kD * 2, cudaMemcpyDeviceToDevice, S.stream));
+    if (nid && S.idmap)
+      CU_TRY(cudaMemcpyAsync(nid, S.idmap, static_cast<size_t>(S.n) * 8, cudaMemcpyDeviceToDevice, S.stream));
+    CU_TRY(cudaStreamSynchronize(S.stream));
+  }
+  dev_free(S.x32); dev_free(S.x16); dev_free(S.idmap);
+  S.x32 = n32; S.x16 = n16; S.idmap = nid; S.cap = ncap;
+  return B2F_OK;
+}
+
+int upload_segs(Shard& S) {
+  const int n = static_cast<int>(S.segs.size());
+  if (n > S.segs_d_cap) {
+    dev_free(S.segs_d);
+    S.segs_d_cap = std::max(16, 2 * n);
+    B2F_TRY(dev_alloc(&S.segs_d, static_cast<size_t>(S.segs_d_cap)));
+  }
+  if (n) CU_TRY(cudaMemcpyAsync(S.segs_d, S.segs.data(), sizeof(Seg) * n, cudaMemcpyHostToDevice, S.stream));
+  return B2F_OK;
+}
+
+void push_seg(Shard& S, int64_t local_start, int64_t count, int64_t global_start) {
+  if (!S.segs.empty()) {
+    Seg& b = S.segs.back();
+    if (b.local_start + b.count == local_start && b.global_start + b.count == global_start) {
+      b.count += count;
+      return;
+    }
+  }
+  S.segs.push_back(Seg{local_start, count, global_start});
+}
+
+int launch_grid_rows(const Shard& S, int64_t rows) {
+  int64_t blocks = (rows + 7) / 8;  // 8 warps per 256-thread block, one row per warp iteration
+  return static_cast<int>(std::min<int64_t>(std::max<int64_t>(blocks, 1), static_cast<int64_t>(S.sm_count) * 8));
+}
+
+// Append rows already resident at x32[S.n .. S.n+n): build shadow + norm bound.
+int ingest_rows(b2f_index* idx, Shard& S, int64_t n) {
+  convert_rows_kernel<<<launch_grid_rows(S, n), 256, 0, S.stream>>>(S.x32, idx->shadow ? S.x16 : nullptr, S.n, n,
+                                                                    S.maxnorm2);
+  CU_TRY(cudaGetLastError());
+  return B2F_OK;
+}
+
+int ensure_query_ws(Shard& S, int64_t nq, int k) {
+  Workspace& W = S.ws;
+  if (nq > W.nq_cap) {
+    dev_free(W.q32); dev_free(W.q16); dev_free(W.qnorm); dev_free(W.ovf_all);
+    if (W.ovf_host) { cudaFreeHost(W.ovf_host); W.ovf_host = nullptr; }
+    const int64_t cap = std::max<int64_t>(nq, 256);
+    B2F_TRY(dev_alloc(&W.q32, static_cast<size_t>(cap) * kD));
+    B2F_TRY(dev_alloc(&W.q16, static_cast<size_t>(cap + kUmmaMaxQ + 16) * kD));
+    B2F_TRY(dev_alloc(&W.qnorm, static_cast<size_t>(cap + kUmmaMaxQ + 16)));
+    B2F_TRY(dev_alloc(&W.ovf_all, static_cast<size_t>(cap)));
+    CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&W.ovf_host), static_cast<size_t>(cap) * sizeof(int)));
+    W.nq_cap = cap;
+  }
+  const int64_t need_out = nq * k;
+  if (need_out > W.out_cap) {
+    dev_free(W.D); dev_free(W.I);
+    B2F_TRY(dev_alloc(&W.D, static_cast<size_t>(need_out)));
+    B2F_TRY(dev_alloc(&W.I, static_cast<size_t>(need_out)));
+    W.out_cap = need_out;
+  }
+  if (!W.fbq) {
+    B2F_TRY(dev_alloc(&W.fbq, static_cast<size_t>(kScanMaxQ) * kD));
+    B2F_TRY(dev_alloc(&W.fbD, static_cast<size_t>(kScanMaxQ) * B2F_MAX_K));
+    B2F_TRY(dev_alloc(&W.fbI, static_cast<size_t>(kScanMaxQ) * B2F_MAX_K));
+  }
+  return B2F_OK;
+}
+
+int ensure_pass_ws(Shard& S, int qp, int C) {
+  Workspace& W = S.ws;
+  if (qp <= W.qp_cap && C <= W.C) return B2F_OK;
+  qp = std::max(qp, W.qp_cap);
+  C = std::max(C, W.C);
+  dev_free(W.cand[0]); dev_free(W.cand[1]); dev_free(W.cnt); dev_free(W.tau); dev_free(W.tauP);
+  dev_free(W.ovf); dev_free(W.margin);
+  B2F_TRY(dev_alloc(&W.cand[0], static_cast<size_t>(qp) * C));
+  B2F_TRY(dev_alloc(&W.cand[1], static_cast<size_t>(qp) * C));
+  B2F_TRY(dev_alloc(&W.cnt, static_cast<size_t>(qp)));
+  B2F_TRY(dev_alloc(&W.tau, static_cast<size_t>(qp)));
+  B2F_TRY(dev_alloc(&W.tauP, static_cast<size_t>(qp)));
+  B2F_TRY(dev_alloc(&W.ovf, static_cast<size_t>(qp)));
+  B2F_TRY(dev_alloc(&W.margin, static_cast<size_t>(qp)));
+  if (!W.err) {
+    B2F_TRY(dev_alloc(&W.err, 1));
+    CU_TRY(cudaMemsetAsync(W.err, 0, sizeof(int), S.stream));
+  }
+  W.qp_cap = qp;
+  W.C = C;
+  return B2F_OK;
+}
+
+int ensure_pin(Shard& S, size_t bytes) {
+  Workspace& W = S.ws;
+  if (bytes <= W.pin_bytes) return B2F_OK;
+  if (W.pin) cudaFreeHost(W.pin);
+  W.pin = nullptr;
+  W.pin_bytes = 0;
+  CU_TRY(cudaMallocHost(&W.pin, bytes));
+  W.pin_bytes = bytes;
+  return B2F_OK;
+}
+
+__global__ void margin_kernel(const float* __restrict__ qnorm, const unsigned int* __restrict__ maxnorm2_bits,
+                              float two_u, int nq, float* __restrict__ margin) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const float pn = __fsqrt_ru(__uint_as_float(*maxnorm2_bits));
+  margin[q] = __fmul_ru(__fmul_ru(qnorm[q], pn), two_u);
+}
+
+__global__ void fill_pad_kernel(float* D, int64_t* I, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) { D[i] = -FLT_MAX; I[i] = -1; }
+}
+
+// Rigorous worst-case error of a score computed from rounded operands / in reduced precision,
+// relative to ||q|| * ||p|| (Cauchy-Schwarz on sum |q_t p_t|):
+//   bf16 engine: two round-to-nearest bf16 operands (2 * 2^-9 + 2^-18) + fp32 accumulation of 768
+//                exact products inside the tensor core (<= 768 * 2^-23) -> 0.004014
+//   fp32 scan  : 24 sequential fma + 5 tree adds, one rounding each -> 29 * 2^-24 < 2^-19
+constexpr double kUBf16 = 0.00390625 * 1.002 + 1.0e-4;
+constexpr double kUScan = 1.9073486328125e-06;
+
+struct PassPlan {
+  int path;     // resolved engine
+  bool exact;   // total-order keys, zero margin, bounded phases
+  int qp;       // max queries per pass
+  int C;        // candidate capacity per query
+  int64_t n0;   // rows of the dense phase
+};
+
+PassPlan make_plan(const b2f_index* idx, const Shard& S, int path, int k) {
+  PassPlan p;
+  p.path = path;
+  p.exact = (path == B2F_PATH_SCAN_EXACT);
+  if (path == B2F_PATH_UMMA_BF16) {
+    p.qp = kUmmaMaxQ;
+    p.n0 = static_cast<int64_t>(S.max_pairs) * kTileRows;  // one wave of pair tiles
+  } else {
+    p.qp = kScanMaxQ;
+    p.n0 = 16384;
+  }
+  p.C = static_cast<int>(std::max<int64_t>(p.n0, 32ll * k));
+  p.C = static_cast<int>(round_up(p.C, 256));
+  return p;
+}
+
+// Enqueue one pass (<= plan.qp queries) on the shard stream.  q32p: the pass's fp32 queries
+// [nqp,768]; q16p: their bf16 copies padded with zero rows (tensor path).  Results go to
+// D_out/I_out with row stride out_stride.
+int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q32p, const __nv_bfloat16* q16p,
+                 const float* qnormp, int nqp, int k, float* D_out, int64_t* I_out, int64_t out_stride,
+                 int* ovf_dst) {
+  Workspace& W = S.ws;
+  Stats& st = idx->stats;
+  const int64_t N = S.n;
+  const int C = W.C;
+  cudaStream_t s = S.stream;
+  CU_TRY(cudaMemsetAsync(W.cnt, 0, sizeof(int) * nqp, s));
+  CU_TRY(cudaMemsetAsync(W.ovf, 0, sizeof(int) * nqp, s));
+  const double u = plan.path == B2F_PATH_UMMA_BF16 ? kUBf16 : kUScan;
+  const float two_u = plan.exact ? 0.f : static_cast<float>(2.0 * u * (idx->margin_ppm * 1e-6) * 1.0000001);
+  margin_kernel<<<(nqp + 127) / 128, 128, 0, s>>>(qnormp, S.maxnorm2, two_u, nqp, W.margin);
+  st.launches += 1;
+
+  int cur = 0;
+  CUtensorMap tmap_p, tmap_q;
+  int n_cols = 0, stages = 0, smem = 0;
+  if (plan.path == B2F_PATH_UMMA_BF16) {
+    n_cols = static_cast<int>(round_up(nqp, 16));
+    stages = umma_stages(n_cols);
+    smem = umma_smem_bytes(n_cols, stages);
+    B2F_TRY(make_tmap_bf16(&tmap_p, S.x16, static_cast<uint64_t>(N), kTileRowsCta));
+    B2F_TRY(make_tmap_bf16(&tmap_q, q16p, static_cast<uint64_t>(n_cols), static_cast<uint32_t>(n_cols / 2)));
+  }
+
+  // Phase boundaries in rows.  Dense phase first, then geometric growth (or, in exact mode,
+  // fixed-size phases that cannot overflow the candidate capacity even if every row passes).
+  int64_t begin = 0;
+  int phase = 0;
+  while (begin < N) {
+    int64_t end;
+    const bool dense = (phase == 0);
+    if (dense) end = std::min<int64_t>(N, plan.n0);
+    else if (plan.exact) end = std::min<int64_t>(N, begin + (C - k));
+    else end = std::min<int64_t>(N, begin * std::max(2, idx->growth));
+    int n_override = -1;
+    if (plan.path == B2F_PATH_UMMA_BF16) {
+      const int tb = static_cast<int>(begin / kTileRows);
+      const int te = static_cast<int>((end + kTileRows - 1) / kTileRows);
+      if (end < N) end = static_cast<int64_t>(te) * kTileRows;  // phases end on tile boundaries
+      UmmaArgs a;
+      a.n_rows = N; a.tile_begin = tb; a.tile_end = te; a.n_cols = n_cols; a.nq = nqp; a.stages = stages;
+      a.dense = dense ? 1 : 0; a.dense_row0 = 0; a.cand = W.cand[cur]; a.cnt = W.cnt; a.C = C;
+      a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
+      const int pairs = std::min(S.max_pairs, te - tb);
+      umma_score_select_kernel<<<2 * pairs, kUmmaThreads, smem, s>>>(tmap_p, tmap_q, a);
+      if (dense) n_override = (te - tb) * kTileRows;
+    } else {
+      ScanArgs a;
+      a.x32 = S.x32; a.row_begin = begin; a.row_end = end; a.q32 = q32p; a.nq_pass = nqp;
+      a.dense = dense ? 1 : 0; a.dense_row0 = 0; a.cand = W.cand[cur]; a.cnt = W.cnt; a.C = C;
+      a.tau = W.tau; a.tauP = W.tauP; a.ovf = W.ovf;
+      const int64_t groups = (end - begin + kScanRows - 1) / kScanRows;
+      const int blocks = static_cast<int>(std::min<int64_t>((groups + 7) / 8, static_cast<int64_t>(S.sm_count)));
+      const size_t sm = scan_smem_bytes(nqp, plan.exact);
+      if (plan.exact) scan_kernel<true><<<std::max(blocks, 1), kScanThreads, sm, s>>>(a);
+      else scan_kernel<false><<<std::max(blocks, 1), kScanThreads, sm, s>>>(a);
+      if (dense) n_override = static_cast<int>(end - begin);
+    }
+    CU_TRY(cudaGetLastError());
+    refresh_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.cnt, C, k, plan.exact ? 1 : 0,
+                                              W.margin, W.tau, W.tauP, n_override);
+    CU_TRY(cudaGetLastError());
+    cur ^= 1;
+    st.launches += 2;
+    st.phases += 1;
+    begin = end;
+    ++phase;
+  }
+  final_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.cnt, C, k, plan.exact ? 0 : 1, q32p,
+                                          S.x32, S.segs_d, static_cast<int>(S.segs.size()),
+                                          S.has_ids ? S.idmap : nullptr, D_out, I_out, out_stride);
+  CU_TRY(cudaGetLastError());
+  st.launches += 1;
+  st.passes += 1;
+  if (ovf_dst) CU_TRY(cudaMemcpyAsync(ovf_dst, W.ovf, sizeof(int) * nqp, cudaMemcpyDeviceToDevice, s));
+  return B2F_OK;
+}
+
+int resolve_path(const b2f_index* idx, const Shard& S, int64_t nq) {
+  int path = idx->path;
+  if (path == B2F_PATH_AUTO) {
+    if (!S.x16) path = B2F_PATH_SCAN_F32;
+    else path = (nq <= idx->scan_max_auto) ? B2F_PATH_SCAN_F32 : B2F_PATH_UMMA_BF16;
+  }
+  if (path == B2F_PATH_UMMA_BF16 && !S.x16) path = B2F_PATH_SCAN_F32;
+  return path;
+}
+
+// Enqueue the whole search of one shard.  q_d: fp32 queries on the shard's device.
+int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d) {
+  CU_TRY(cudaSetDevice(S.dev));
+  Workspace& W = S.ws;
+  cudaStream_t s = S.stream;
+  if (S.n == 0) {
+    fill_pad_kernel<<<static_cast<int>((nq * k + 255) / 256), 256, 0, s>>>(D_d, I_d, nq * k);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemsetAsync(W.ovf_all, 0, sizeof(int) * nq, s));
+    return B2F_OK;
+  }
+  const int path = resolve_path(idx, S, nq);
+  idx->stats.path = path;
+  const PassPlan plan = make_plan(idx, S, path, k);
+  B2F_TRY(ensure_pass_ws(S, plan.qp, plan.C));
+  B2F_TRY(upload_segs(S));
+  const int64_t nq_pad = round_up(nq, 16) + kUmmaMaxQ;
+  prep_queries_kernel<<<static_cast<int>((nq_pad * 32 + 127) / 128), 128, 0, s>>>(
+      q_d, static_cast<int>(nq), static_cast<int>(nq_pad), W.q16, W.qnorm);
+  CU_TRY(cudaGetLastError());
+  idx->stats.launches += 1;
+  if (plan.path == B2F_PATH_UMMA_BF16) {
+    static bool attr_set[64] = {false};
+    if (!attr_set[S.dev & 63]) {
+      CU_TRY(cudaFuncSetAttribute(umma_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+      attr_set[S.dev & 63] = true;
+    }
+  } else {
+    static bool attr_set2[64] = {false};
+    if (!attr_set2[S.dev & 63]) {
+      CU_TRY(cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      CU_TRY(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      attr_set2[S.dev & 63] = true;
+    }
+  }
+  for (int64_t q0 = 0; q0 < nq; q0 += plan.qp) {
+    const int nqp = static_cast<int>(std::min<int64_t>(plan.qp, nq - q0));
+    B2F_TRY(enqueue_pass(idx, S, plan, q_d + q0 * kD, W.q16 + q0 * kD, W.qnorm + q0, nqp, k, D_d + q0 * k,
+                         I_d + q0 * k, k, W.ovf_all + q0));
+  }
+  CU_TRY(cudaMemcpyAsync(W.ovf_host, W.ovf_all, sizeof(int) * nq, cudaMemcpyDeviceToHost, s));
+  return B2F_OK;
+}
+
+// After the stream drained: re-run any query whose candidate list overflowed on the exact engine
+// (bounded phases, cannot overflow).  Normally a no-op.
+int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d) {
+  CU_TRY(cudaSetDevice(S.dev));
+  CU_TRY(cudaStreamSynchronize(S.stream));
+  if (S.n == 0) return B2F_OK;
+  Workspace& W = S.ws;
+  std::vector<int64_t> bad;
+  for (int64_t q = 0; q < nq; ++q)
+    if (W.ovf_host[q]) bad.push_back(q);
+  if (bad.empty()) return B2F_OK;
+  idx->stats.fallback_queries += static_cast<double>(bad.size());
+  static bool attr_set3[64] = {false};
+  if (!attr_set3[S.dev & 63]) {
+    CU_TRY(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    attr_set3[S.dev & 63] = true;
+  }
+  const PassPlan plan = make_plan(idx, S, B2F_PATH_SCAN_EXACT, k);
+  B2F_TRY(ensure_pass_ws(S, plan.qp, plan.C));
+  cudaStream_t s = S.stream;
+  for (size_t b0 = 0; b0 < bad.size(); b0 += kScanMaxQ) {
+    const int nb = static_cast<int>(std::min<size_t>(kScanMaxQ, bad.size() - b0));
+    for (int i = 0; i < nb; ++i)
+      CU_TRY(cudaMemcpyAsync(W.fbq + static_cast<size_t>(i) * kD, q_d + bad[b0 + i] * kD, kD * 4,
+                             cudaMemcpyDeviceToDevice, s));
+    B2F_TRY(enqueue_pass(idx, S, plan, W.fbq, nullptr, W.qnorm /*unused: exact*/, nb, k, W.fbD, W.fbI, k, nullptr));
+    for (int i = 0; i < nb; ++i) {
+      CU_TRY(cudaMemcpyAsync(D_d + bad[b0 + i] * k, W.fbD + static_cast<size_t>(i) * k, sizeof(float) * k,
+                             cudaMemcpyDeviceToDevice, s));
+      CU_TRY(cudaMemcpyAsync(I_d + bad[b0 + i] * k, W.fbI + static_cast<size_t>(i) * k, sizeof(int64_t) * k,
+                             cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  CU_TRY(cudaStreamSynchronize(s));
+  return B2F_OK;
+}
+
+int check_args_search(const b2f_index* idx, const void* q, int64_t nq, int k, const void* D, const void* I) {
+  if (!idx) return fail(B2F_ERR_INVALID, "null index");
+  if (nq < 0) return fail(B2F_ERR_INVALID, "negative query count");
+  if (k < 1 || k > B2F_MAX_K) return fail(B2F_ERR_INVALID, "k must be in [1, " + std::to_string(B2F_MAX_K) + "], got " + std::to_string(k));
+  if (nq > 0 && (!q || !D || !I)) return fail(B2F_ERR_INVALID, "null query or output pointer");
+  return B2F_OK;
+}
+
+void reset_stats(b2f_index* idx) { idx->stats = Stats(); }
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* b2f_last_error(void) { return g_err.c_str(); }
+const char* b2f_version(void) { return "b2f 0.1 sm_100a"; }
+
+int b2f_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int b2f_create(int d, const int* devices, int n_dev, b2f_index** out) {
+  if (!out) return fail(B2F_ERR_INVALID, "null out pointer");
+  *out = nullptr;
+  if (d != kD) return fail(B2F_ERR_INVALID, "only d = 768 is supported (reference hard-codes IndexFlatIP(768)), got " + std::to_string(d));
+  const int avail = b2f_device_count();
+  if (avail <= 0) return fail(B2F_ERR_NO_DEVICE, "no CUDA device available; b2f has no CPU fallback");
+  std::vector<int> devs;
+  if (!devices || n_dev <= 0) devs.push_back(0);
+  else devs.assign(devices, devices + n_dev);
+  for (int dv : devs)
+    if (dv < 0 || dv >= avail) return fail(B2F_ERR_INVALID, "device " + std::to_string(dv) + " out of range");
+  b2f_index* idx = new b2f_index();
+  idx->shards.resize(devs.size());
+  for (size_t i = 0; i < devs.size(); ++i) {
+    Shard& S = idx->shards[i];
+    S.dev = devs[i];
+    cudaDeviceProp prop;
+    cudaError_t e = cudaSetDevice(S.dev);
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, S.dev);
+    if (e == cudaSuccess && prop.major != 10) {
+      b2f_destroy(idx);
+      return fail(B2F_ERR_NO_DEVICE, "device " + std::to_string(S.dev) + " is sm_" + std::to_string(prop.major) +
+                                         std::to_string(prop.minor) + "; b2f is built for sm_100a only");
+    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&S.maxnorm2), sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(S.maxnorm2, 0, sizeof(unsigned int));
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      std::string m = std::string("device setup failed: ") + cudaGetErrorString(e);
+      b2f_destroy(idx);
+      return fail(B2F_ERR_CUDA, m);
+    }
+    S.sm_count = prop.multiProcessorCount;
+    S.max_pairs = std::max(1, S.sm_count / 2);
+  }
+  // peer access between shard devices (direct NVLink copies for the result gather)
+  for (size_t i = 0; i < devs.size(); ++i)
+    for (size_t j = 0; j < devs.size(); ++j) {
+      if (i == j) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) == cudaSuccess && can) {
+        cudaSetDevice(devs[i]);
+        cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
+        if (e != cudaSuccess) (void)cudaGetLastError();
+      }
+    }
+  *out = idx;
+  return B2F_OK;
+}
+
+void b2f_destroy(b2f_index* idx) {
+  if (!idx) return;
+  for (Shard& S : idx->shards) {
+    cudaSetDevice(S.dev);
+    if (S.stream) cudaStreamSynchronize(S.stream);
+    Workspace& W = S.ws;
+    dev_free(S.x32); dev_free(S.x16); dev_free(S.idmap); dev_free(S.maxnorm2); dev_free(S.segs_d);
+    dev_free(W.cand[0]); dev_free(W.cand[1]); dev_free(W.cnt); dev_free(W.tau); dev_free(W.tauP);
+    dev_free(W.ovf); dev_free(W.margin); dev_free(W.err); dev_free(W.q32); dev_free(W.q16);
+    dev_free(W.qnorm); dev_free(W.ovf_all); dev_free(W.D); dev_free(W.I); dev_free(W.Dp); dev_free(W.Ip);
+    dev_free(W.fbq); dev_free(W.fbD); dev_free(W.fbI);
+    if (W.ovf_host) cudaFreeHost(W.ovf_host);
+    if (W.pin) cudaFreeHost(W.pin);
+    if (S.ev) cudaEventDestroy(S.ev);
+    if (S.stream) cudaStreamDestroy(S.stream);
+  }
+  (void)cudaGetLastError();
+  delete idx;
+}
+
+int64_t b2f_ntotal(const b2f_index* idx) { return idx ? idx->ntotal : -1; }
+int b2f_num_shards(const b2f_index* idx) { return idx ? static_cast<int>(idx->shards.size()) : 0; }
+int64_t b2f_shard_rows(const b2f_index* idx, int shard) {
+  if (!idx || shard < 0 || shard >= static_cast<int>(idx->shards.size())) return -1;
+  return idx->shards[shard].n;
+}
+void* b2f_stream(b2f_index* idx, int shard) {
+  if (!idx || shard < 0 || shard >= static_cast<int>(idx->shards.size())) return nullptr;
+  return idx->shards[shard].stream;
+}
+
+int b2f_reserve(b2f_index* idx, int64_t n_per_shard) {
+  if (!idx || n_per_shard < 0) return fail(B2F_ERR_INVALID, "bad reserve arguments");
+  if (n_per_shard >= 0xfffffff0ll) return fail(B2F_ERR_INVALID, "a shard holds at most 2^32-16 rows");
+  for (Shard& S : idx->shards) B2F_TRY(ensure_capacity(idx, S, n_per_shard));
+  return B2F_OK;
+}
+
+static int add_impl(b2f_index* idx, const float* x_host, const int64_t* ids_host, int64_t n) {
+  if (!idx) return fail(B2F_ERR_INVALID, "null index");
+  if (n < 0 || (n > 0 && !x_host)) return fail(B2F_ERR_INVALID, "bad add arguments");
+  if (n == 0) return B2F_OK;
+  const int G = static_cast<int>(idx->shards.size());
+  if (ids_host) {
+    for (Shard& S : idx->shards)
+      if (S.n > 0 && !S.has_ids) return fail(B2F_ERR_INVALID, "cannot mix add() and add_with_ids() on a non-empty index");
+  } else {
+    for (Shard& S : idx->shards)
+      if (S.has_ids && S.n > 0) return fail(B2F_ERR_INVALID, "cannot mix add_with_ids() and add() on a non-empty index");
+  }
+  // contiguous split, like FAISS IndexShards with successive ids
+  for (int g = 0; g < G; ++g) {
+    Shard& S = idx->shards[g];
+    const int64_t lo = n * g / G, hi = n * (g + 1) / G, m = hi - lo;
+    if (m == 0) continue;
+    CU_TRY(cudaSetDevice(S.dev));
+    if (ids_host && !S.has_ids) {
+      S.has_ids = true;
+      if (S.cap > 0 && !S.idmap) B2F_TRY(dev_alloc(&S.idmap, static_cast<size_t>(S.cap)));
+    }
+    if (!ids_host) S.has_ids = false;
+    if (S.n + m >= 0xfffffff0ll) return fail(B2F_ERR_INVALID, "a shard holds at most 2^32-16 rows");
+    B2F_TRY(ensure_capacity(idx, S, S.n + m));
+    CU_TRY(cudaMemcpyAsync(S.x32 + S.n * kD, x_host + lo * kD, static_cast<size_t>(m) * kD * 4,
+                           cudaMemcpyHostToDevice, S.stream));
+    if (ids_host)
+      CU_TRY(cudaMemcpyAsync(S.idmap + S.n, ids_host + lo, static_cast<size_t>(m) * 8, cudaMemcpyHostToDevice, S.stream));
+    B2F_TRY(ingest_rows(idx, S, m));
+    push_seg(S, S.n, m, idx->ntotal + lo);
+    S.n += m;
+  }
+  for (Shard& S : idx->shards) {
+    CU_TRY(cudaSetDevice(S.dev));
+    CU_TRY(cudaStreamSynchronize(S.stream));  // FAISS add() is synchronous: the caller may free x now
+  }
+  idx->ntotal += n;
+  return B2F_OK;
+}
+
+int b2f_add(b2f_index* idx, const float* x_host, int64_t n) { return add_impl(idx, x_host, nullptr, n); }
+int b2f_add_with_ids(b2f_index* idx, const float* x_host, const int64_t* ids_host, int64_t n) {
+  if (n > 0 && !ids_host) return fail(B2F_ERR_INVALID, "null ids");
+  return add_impl(idx, x_host, ids_host, n);
+}
+
+int b2f_add_device(b2f_index* idx, int shard, const float* x_dev, int64_t n) {
+  if (!idx || shard < 0 || shard >= static_cast<int>(idx->shards.size()) || n < 0 || (n > 0 && !x_dev))
+    return fail(B2F_ERR_INVALID, "bad add_device arguments");
+  if (n == 0) return B2F_OK;
+  Shard& S = idx->shards[shard];
+  if (S.has_ids && S.n > 0) return fail(B2F_ERR_INVALID, "index uses explicit ids");
+  CU_TRY(cudaSetDevice(S.dev));
+  B2F_TRY(ensure_capacity(idx, S, S.n + n));
+  CU_TRY(cudaMemcpyAsync(S.x32 + S.n * kD, x_dev, static_cast<size_t>(n) * kD * 4, cudaMemcpyDeviceToDevice, S.stream));
+  B2F_TRY(ingest_rows(idx, S, n));
+  push_seg(S, S.n, n, idx->ntotal);
+  S.n += n;
+  idx->ntotal += n;
+  CU_TRY(cudaStreamSynchronize(S.stream));
+  return B2F_OK;
+}
+
+int b2f_add_synthetic(b2f_index* idx, int shard, int64_t first_row, int64_t n, uint64_t seed, uint64_t stream,
+                      float norm, int64_t id_base) {
+  if (!idx || shard < 0 || shard >= static_cast<int>(idx->shards.size()) || n < 0 || first_row < 0)
+    return fail(B2F_ERR_INVALID, "bad add_synthetic arguments");
+  if (n == 0) return B2F_OK;
+  Shard& S = idx->shards[shard];
+  if (S.has_ids && S.n > 0) return fail(B2F_ERR_INVALID, "index uses explicit ids");
+  CU_TRY(cudaSetDevice(S.dev));
+  B2F_TRY(ensure_capacity(idx, S, S.n + n));
+  const uint32_t k0 = static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(stream);
+  const uint32_t k1 = static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(stream >> 32) ^ 0x5eedu;
+  synth_rows_kernel<<<launch_grid_rows(S, n), 256, 0, S.stream>>>(S.x32, idx->shadow ? S.x16 : nullptr, S.n,
+                                                                  first_row, n, k0, k1, norm, S.maxnorm2);
+  CU_TRY(cudaGetLastError());
+  push_seg(S, S.n, n, id_base);
+  S.n += n;
+  idx->ntotal += n;
+  CU_TRY(cudaStreamSynchronize(S.stream));
+  return B2F_OK;
+}
+
+int b2f_reconstruct_n(b2f_index* idx, int shard, int64_t row0, int64_t n, float* out_host) {
+  if (!idx || shard < 0 || shard >= static_cast<int>(idx->shards.size()) || row0 < 0 || n < 0 || (n > 0 && !out_host))
+    return fail(B2F_ERR_INVALID, "bad reconstruct_n arguments");
+  Shard& S = idx->shards[shard];
+  if (row0 + n > S.n) return fail(B2F_ERR_INVALID, "reconstruct_n range exceeds the shard's rows");
+  if (n == 0) return B2F_OK;
+  CU_TRY(cudaSetDevice(S.dev));
+  CU_TRY(cudaMemcpyAsync(out_host, S.x32 + row0 * kD, static_cast<size_t>(n) * kD * 4, cudaMemcpyDeviceToHost, S.stream));
+  CU_TRY(cudaStreamSynchronize(S.stream));
+  return B2F_OK;
+}
+
+int b2f_reset(b2f_index* idx) {
+  if (!idx) return fail(B2F_ERR_INVALID, "null index");
+  for (Shard& S : idx->shards) {
+    CU_TRY(cudaSetDevice(S.dev));
+    CU_TRY(cudaStreamSynchronize(S.stream));
+    S.n = 0;
+    S.segs.clear();
+    S.has_ids = false;
+    CU_TRY(cudaMemsetAsync(S.maxnorm2, 0, sizeof(unsigned int), S.stream));
+    if (!idx->keep_on_reset) {
+      dev_free(S.x32); dev_free(S.x16); dev_free(S.idmap);
+      S.cap = 0;
+    }
+  }
+  idx->ntotal = 0;
+  return B2F_OK;
+}
+
+int b2f_search_device(b2f_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+  B2F_TRY(check_args_search(idx, q_dev, nq, k, D_dev, I_dev));
+  if (idx->shards.size() != 1) return fail(B2F_ERR_INVALID, "b2f_search_device needs a single-shard index");
+  if (nq == 0) return B2F_OK;
+  reset_stats(idx);
+  Shard& S = idx->shards[0];
+  CU_TRY(cudaSetDevice(S.dev));
+  B2F_TRY(ensure_query_ws(S, nq, k));
+  B2F_TRY(enqueue_search(idx, S, q_dev, nq, k, D_dev, I_dev));
+  B2F_TRY(finish_search(idx, S, q_dev, nq, k, D_dev, I_dev));
+  return B2F_OK;
+}
+
+int b2f_merge_device(b2f_index* idx, const float* D_parts_dev, const int64_t* I_parts_dev, int n_parts,
+                     int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+  if (!idx || n_parts < 1 || nq < 0 || k < 1 || !D_parts_dev || !I_parts_dev || !D_dev || !I_dev)
+    return fail(B2F_ERR_INVALID, "bad merge arguments");
+  if (nq == 0) return B2F_OK;
+  Shard& S = idx->shards[0];
+  CU_TRY(cudaSetDevice(S.dev));
+  merge_kernel<<<static_cast<int>(nq), 256, 0, S.stream>>>(D_parts_dev, I_parts_dev, n_parts, nq, k, D_dev, I_dev);
+  CU_TRY(cudaGetLastError());
+  idx->stats.launches += 1;
+  CU_TRY(cudaStreamSynchronize(S.stream));
+  return B2F_OK;
+}
+
+int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_host, int64_t* I_host) {
+  B2F_TRY(check_args_search(idx, q_host, nq, k, D_host, I_host));
+  if (nq == 0) return B2F_OK;
+  reset_stats(idx);
+  const int G = static_cast<int>(idx->shards.size());
+  const size_t qbytes = static_cast<size_t>(nq) * kD * 4;
+  const size_t d_off = static_cast<size_t>(round_up(static_cast<int64_t>(nq) * k * 4, 16));
+  const size_t obytes = d_off + static_cast<size_t>(nq) * k * sizeof(int64_t);  // pinned layout [D | pad | I]
+  Shard& S0 = idx->shards[0];
+  // stage the queries once in pinned memory, then upload to every shard
+  CU_TRY(cudaSetDevice(S0.dev));
+  B2F_TRY(ensure_pin(S0, std::max(qbytes, obytes)));
+  std::memcpy(S0.ws.pin, q_host, qbytes);
+  for (int g = 0; g < G; ++g) {
+    Shard& S = idx->shards[g];
+    CU_TRY(cudaSetDevice(S.dev));
+    B2F_TRY(ensure_query_ws(S, nq, k));
+    CU_TRY(cudaMemcpyAsync(S.ws.q32, S0.ws.pin, qbytes, cudaMemcpyHostToDevice, S.stream));
+    B2F_TRY(enqueue_search(idx, S, S.ws.q32, nq, k, S.ws.D, S.ws.I));
+  }
+  for (int g = 0; g < G; ++g) {
+    Shard& S = idx->shards[g];
+    B2F_TRY(finish_search(idx, S, S.ws.q32, nq, k, S.ws.D, S.ws.I));
+  }
+  CU_TRY(cudaSetDevice(S0.dev));
+  const float* Dres = S0.ws.D;
+  const int64_t* Ires = S0.ws.I;
+  if (G > 1) {
+    Workspace& W = S0.ws;
+    const int64_t per = nq * k;
+    if (per * (G + 1) > W.parts_cap) {
+      dev_free(W.Dp); dev_free(W.Ip);
+      B2F_TRY(dev_alloc(&W.Dp, static_cast<size_t>(per) * (G + 1)));
+      B2F_TRY(dev_alloc(&W.Ip, static_cast<size_t>(per) * (G + 1)));
+      W.parts_cap = per * (G + 1);
+    }
+    for (int g = 0; g < G; ++g) {
+      Shard& S = idx->shards[g];
+      CU_TRY(cudaMemcpyPeerAsync(W.Dp + per * g, S0.dev, S.ws.D, S.dev, sizeof(float) * per, S0.stream));
+      CU_TRY(cudaMemcpyPeerAsync(W.Ip + per * g, S0.dev, S.ws.I, S.dev, sizeof(int64_t) * per, S0.stream));
+    }
+    merge_kernel<<<static_cast<int>(nq), 256, 0, S0.stream>>>(W.Dp, W.Ip, G, nq, k, W.Dp + per * G, W.Ip + per * G);
+    CU_TRY(cudaGetLastError());
+    idx->stats.launches += 1;
+    Dres = W.Dp + per * G;
+    Ires = W.Ip + per * G;
+  }
+  float* pinD = reinterpret_cast<float*>(S0.ws.pin);
+  int64_t* pinI = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(S0.ws.pin) + d_off);
+  CU_TRY(cudaMemcpyAsync(pinD, Dres, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
+  CU_TRY(cudaMemcpyAsync(pinI, Ires, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
+  CU_TRY(cudaStreamSynchronize(S0.stream));
+  std::memcpy(D_host, pinD, sizeof(float) * nq * k);
+  std::memcpy(I_host, pinI, sizeof(int64_t) * nq * k);
+  return B2F_OK;
+}
+
+int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
+  if (!idx || !key) return fail(B2F_ERR_INVALID, "bad option arguments");
+  const std::string k(key);
+  if (k == "path") {
+    if (value < 0 || value > 3) return fail(B2F_ERR_INVALID, "path must be 0..3");
+    idx->path = static_cast<int>(value);
+  } else if (k == "shadow") {
+    if (idx->ntotal > 0) return fail(B2F_ERR_INVALID, "shadow can only be changed on an empty index");
+    idx->shadow = value ? 1 : 0;
+    if (!idx->shadow)
+      for (Shard& S : idx->shards) { cudaSetDevice(S.dev); dev_free(S.x16); }
+    else
+      for (Shard& S : idx->shards) { cudaSetDevice(S.dev); dev_free(S.x32); dev_free(S.x16); dev_free(S.idmap); S.cap = 0; }
+  } else if (k == "growth") {
+    if (value < 2 || value > 1024) return fail(B2F_ERR_INVALID, "growth must be in [2, 1024]");
+    idx->growth = static_cast<int>(value);
+  } else if (k == "margin_ppm") {
+    if (value < 0) return fail(B2F_ERR_INVALID, "margin_ppm must be >= 0");
+    idx->margin_ppm = value;
+  } else if (k == "keep_on_reset") {
+    idx->keep_on_reset = value ? 1 : 0;
+  } else if (k == "scan_max_auto") {
+    if (value < 0 || value > kScanMaxQ) return fail(B2F_ERR_INVALID, "scan_max_auto must be in [0, 32]");
+    idx->scan_max_auto = static_cast<int>(value);
+  } else {
+    return fail(B2F_ERR_INVALID, "unknown option '" + k + "'");
+  }
+  return B2F_OK;
+}
+
+int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
+  if (!idx || !key || !out) return fail(B2F_ERR_INVALID, "bad stat arguments");
+  const std::string k(key);
+  const Stats& s = idx->stats;
+  if (k == "launches") *out = s.launches;
+  else if (k == "phases") *out = s.phases;
+  else if (k == "candidates") *out = s.candidates;
+  else if (k == "fallback_queries") *out = s.fallback_queries;
+  else if (k == "path") *out = s.path;
+  else if (k == "passes") *out = s.passes;
+  else return fail(B2F_ERR_INVALID, "unknown stat '" + k + "'");
+  return B2F_OK;
+}
+
+}  // extern "C"

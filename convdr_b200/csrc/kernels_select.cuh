@@ -1,0 +1,274 @@
+// kernels_select.cuh — candidate-list maintenance: threshold refresh (radix select + compaction),
+// exact rescoring + final sort, and the cross-shard merge.
+//
+// Replaces, on device, what the reference does in interpreted Python after every block:
+// `passage_embedding2id[I]`, tuple building and the 2-way sorted merge
+// (drivers/run_convdr_inference.py:190-229), and what FAISS does inside search
+// (heap / BlockSelect top-k, IndexShards CPU merge).
+#pragma once
+#include "common.cuh"
+
+namespace b2f {
+
+constexpr int kSelThreads = 256;
+constexpr int kSortCap = 2048;  // == B2F_MAX_K
+
+struct Seg {  // rows [local_start, local_start+count) of a shard carry ids global_start + i
+  int64_t local_start, count, global_start;
+};
+
+struct SelectSmem {
+  unsigned int hist[256];
+  unsigned int warp_tot[kSelThreads / 32];
+  unsigned int digit, remaining, count, nvalid;
+};
+
+// Inclusive prefix sum over the block (256 threads), value per thread.
+__device__ __forceinline__ unsigned int block_inclusive_scan(unsigned int v, SelectSmem& sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    unsigned int t = __shfl_up_sync(0xffffffffu, v, s);
+    if (lane >= s) v += t;
+  }
+  if (lane == 31) sm.warp_tot[warp] = v;
+  __syncthreads();
+  unsigned int base = 0;
+  for (int w = 0; w < warp; ++w) base += sm.warp_tot[w];
+  __syncthreads();
+  return v + base;
+}
+
+// Top (8*passes) bits of the k-th largest record of in[0..n).  Requires >= k non-zero records.
+__device__ uint64_t block_kth_prefix(const uint64_t* __restrict__ in, int n, int k, int passes,
+                                     SelectSmem& sm) {
+  uint64_t prefix = 0, mask = 0;
+  unsigned int remaining = static_cast<unsigned int>(k);
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = 56 - 8 * pass;
+    sm.hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kSelThreads) {
+      const uint64_t key = in[i];
+      if ((key & mask) == prefix) atomicAdd(&sm.hist[static_cast<unsigned int>(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    const unsigned int h = sm.hist[255 - threadIdx.x];  // thread t owns bucket 255-t (descending)
+    const unsigned int cum = block_inclusive_scan(h, sm);
+    if (cum >= remaining && cum - h < remaining) {
+      sm.digit = 255u - threadIdx.x;
+      sm.remaining = remaining - (cum - h);
+    }
+    __syncthreads();
+    prefix |= static_cast<uint64_t>(sm.digit) << shift;
+    mask |= 0xffull << shift;
+    remaining = sm.remaining;
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__device__ int block_count_valid(const uint64_t* __restrict__ in, int n, SelectSmem& sm) {
+  if (threadIdx.x == 0) sm.nvalid = 0;
+  __syncthreads();
+  unsigned int c = 0;
+  for (int i = threadIdx.x; i < n; i += kSelThreads) c += (in[i] != 0ull);
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sm.nvalid, c);
+  __syncthreads();
+  const int r = static_cast<int>(sm.nvalid);
+  __syncthreads();
+  return r;
+}
+
+// Copy every non-empty record >= T from in[0..n) to out[0..); returns how many.  Order arbitrary.
+__device__ int block_compact(const uint64_t* __restrict__ in, int n, uint64_t T,
+                             uint64_t* __restrict__ out, SelectSmem& sm) {
+  if (threadIdx.x == 0) sm.count = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += kSelThreads) {
+    const int i = i0 + threadIdx.x;
+    const uint64_t key = (i < n) ? in[i] : 0ull;
+    const bool keep = key != 0ull && key >= T;
+    const unsigned int b = __ballot_sync(0xffffffffu, keep);
+    if (b) {
+      const int lane = threadIdx.x & 31;
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(&sm.count, __popc(b));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (keep) out[base + __popc(b & ((1u << lane) - 1u))] = key;
+    }
+  }
+  __syncthreads();
+  const int m = static_cast<int>(sm.count);
+  __syncthreads();
+  return m;
+}
+
+// Threshold refresh between phases, one block per query of the pass.
+//   approx mode (exact == 0): tau = (k-th largest approximate score) - margin[q], rounded down;
+//       survivors are the records with score >= tau.  Any true top-k row has an approximate score
+//       within margin/2 of its exact score, so it survives (DESIGN.md "exactness argument").
+//   exact mode: scores are final; tauP = the k-th largest record, survivors are exactly the top k.
+// With fewer than k valid records nothing can be rejected yet (tau = -inf / tauP = 0).
+__global__ void __launch_bounds__(kSelThreads) refresh_kernel(
+    const uint64_t* __restrict__ cand_in, uint64_t* __restrict__ cand_out, int* __restrict__ cnt,
+    int C, int k, int exact, const float* __restrict__ margin, float* __restrict__ tau,
+    uint64_t* __restrict__ tauP, int n_override) {
+  __shared__ SelectSmem sm;
+  const int q = blockIdx.x;
+  const uint64_t* in = cand_in + static_cast<int64_t>(q) * C;
+  uint64_t* out = cand_out + static_cast<int64_t>(q) * C;
+  int n = n_override >= 0 ? n_override : cnt[q];
+  if (n > C) n = C;
+  const int nvalid = block_count_valid(in, n, sm);
+  uint64_t T = 0ull;
+  float t = -INFINITY;
+  if (nvalid >= k) {
+    const uint64_t prefix = block_kth_prefix(in, n, k, exact ? 8 : 4, sm);
+    if (exact) {
+      T = prefix;
+      t = key2f(static_cast<uint32_t>(prefix >> 32));
+    } else {
+      t = __fsub_rd(key2f(static_cast<uint32_t>(prefix >> 32)), margin[q]);
+      T = static_cast<uint64_t>(fkey(t)) << 32;
+    }
+  }
+  const int m = block_compact(in, n, T, out, sm);
+  if (threadIdx.x == 0) {
+    cnt[q] = m;
+    tau[q] = t;
+    tauP[q] = T;
+  }
+}
+
+__device__ __forceinline__ int64_t row_to_id(uint32_t row, const Seg* __restrict__ segs, int nseg,
+                                             const int64_t* __restrict__ idmap) {
+  if (idmap) return idmap[row];
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) {  // last segment with local_start <= row
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].local_start <= static_cast<int64_t>(row)) lo = mid; else hi = mid - 1;
+  }
+  return segs[lo].global_start + (static_cast<int64_t>(row) - segs[lo].local_start);
+}
+
+// Final step of a pass, one block per query: exact rescoring of the surviving candidates
+// (fp64-accumulated dot, one warp per candidate), top-k by total order, sorted output.
+//   D_out / I_out: row stride `out_stride`, k entries written per query.
+__global__ void __launch_bounds__(kSelThreads) final_kernel(
+    uint64_t* __restrict__ cand_cur, uint64_t* __restrict__ cand_other, const int* __restrict__ cnt,
+    int C, int k, int rescore, const float* __restrict__ q32 /* pass queries [nq_pass, 768] */,
+    const float* __restrict__ x32, const Seg* __restrict__ segs, int nseg,
+    const int64_t* __restrict__ idmap, float* __restrict__ D_out, int64_t* __restrict__ I_out,
+    int64_t out_stride) {
+  __shared__ SelectSmem sm;
+  __shared__ __align__(16) float Qs[kD];
+  __shared__ uint64_t sortbuf[kSortCap];
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int n = cnt[q];
+  if (n > C) n = C;
+  uint64_t* src = cand_cur + static_cast<int64_t>(q) * C;
+  uint64_t* dst = cand_other + static_cast<int64_t>(q) * C;
+  if (rescore) {
+    for (int i = threadIdx.x; i < kD; i += kSelThreads) Qs[i] = q32[static_cast<int64_t>(q) * kD + i];
+    __syncthreads();
+    const float4* q4 = reinterpret_cast<const float4*>(Qs);
+    for (int c = warp; c < n; c += kSelThreads / 32) {
+      const uint64_t rec = src[c];
+      uint64_t o = 0ull;
+      if (rec != 0ull) {  // warp-uniform
+        const uint32_t row = cand_row(rec);
+        const float s = exact_dot_warp(q4, reinterpret_cast<const float4*>(x32 + static_cast<int64_t>(row) * kD), lane);
+        o = pack_cand(s, row);
+      }
+      if (lane == 0) dst[c] = o;
+    }
+    __syncthreads();
+    uint64_t* t = src; src = dst; dst = t;
+  }
+  if (n > kSortCap) {
+    const int nvalid = block_count_valid(src, n, sm);
+    uint64_t T = 0ull;
+    if (nvalid >= k) T = block_kth_prefix(src, n, k, 8, sm);
+    n = block_compact(src, n, T, dst, sm);  // == min(nvalid, k) <= kSortCap
+    uint64_t* t = src; src = dst; dst = t;
+  }
+  int P = 32;
+  while (P < n) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += kSelThreads) sortbuf[i] = (i < n) ? src[i] : 0ull;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (P >> 1); i += kSelThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t a = sortbuf[lo], b = sortbuf[hi];
+        if ((a < b) == desc) { sortbuf[lo] = b; sortbuf[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k; i += kSelThreads) {
+    const uint64_t rec = (i < P) ? sortbuf[i] : 0ull;
+    float s = -3.402823466e+38f;
+    int64_t id = -1;
+    if (rec != 0ull) {
+      s = cand_score(rec);
+      id = row_to_id(cand_row(rec), segs, nseg, idmap);
+    }
+    D_out[static_cast<int64_t>(q) * out_stride + i] = s;
+    I_out[static_cast<int64_t>(q) * out_stride + i] = id;
+  }
+}
+
+// Cross-shard merge: parts [G][nq][k] (each sorted by score desc, padded with id = -1) -> [nq][k].
+// Rank-by-counting: an element's output position is its position in its own list plus, for every
+// other list, the number of elements that precede it; ties go to the earlier part, then the earlier
+// position (the reference's merge keeps the earlier block on `>=`, :218).
+__global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ Dp,
+                                                    const int64_t* __restrict__ Ip, int G, int64_t nq,
+                                                    int k, float* __restrict__ D, int64_t* __restrict__ I) {
+  const int64_t q = blockIdx.x;
+  __shared__ int total_valid;
+  if (threadIdx.x == 0) total_valid = 0;
+  __syncthreads();
+  const int E = G * k;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int g = e / k, i = e - g * k;
+    const int64_t base = (static_cast<int64_t>(g) * nq + q) * k;
+    const int64_t id = Ip[base + i];
+    if (id < 0) continue;
+    atomicAdd(&total_valid, 1);
+    const float s = Dp[base + i];
+    int rank = i;
+    for (int g2 = 0; g2 < G; ++g2) {
+      if (g2 == g) continue;
+      const int64_t b2 = (static_cast<int64_t>(g2) * nq + q) * k;
+      // count valid elements of list g2 that precede (s): score > s, or == s when g2 < g
+      int lo = 0, hi = k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const bool valid = Ip[b2 + mid] >= 0;
+        const float s2 = Dp[b2 + mid];
+        const bool before = valid && (s2 > s || (s2 == s && g2 < g));
+        if (before) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      D[q * k + rank] = s;
+      I[q * k + rank] = id;
+    }
+  }
+  __syncthreads();
+  for (int i = total_valid + threadIdx.x; i < k; i += blockDim.x) {
+    D[q * k + i] = -3.402823466e+38f;
+    I[q * k + i] = -1;
+  }
+}
+
+}  // namespace b2f

@@ -1,0 +1,186 @@
+"""Host-side index object over the C ABI (include/b2f.h).
+
+Mirrors the slice of `faiss.IndexFlatIP` that ConvDR's inference driver uses
+(reference drivers/run_convdr_inference.py:180 `add`, :182 `search`, :202 `reset`, :353 ctor),
+with the same argument meaning and error behaviour: float32 row-major inputs, results as fresh
+numpy arrays `D float32 [nq,k]` (descending) and `I int64 [nq,k]`, `-1` / `-FLT_MAX` padding,
+`RuntimeError` for engine failures, `AssertionError` for shape mismatches.
+
+All arithmetic happens in libb2f.so on the GPU.  There is no CPU path in this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+PATHS = {"auto": 0, "scan_f32": 1, "scan_exact": 2, "umma_bf16": 3}
+DIM = 768
+MAX_K = 2048
+
+
+def get_num_gpus() -> int:
+    """faiss.get_num_gpus() (reference :327)."""
+    return int(_lib.load().b2f_device_count())
+
+
+class FlatIPIndex:
+    """Exact inner-product index resident on one or more B200s."""
+
+    def __init__(self, d: int = DIM, devices: Optional[Sequence[int]] = None):
+        self.d = int(d)
+        self.is_trained = True
+        self.metric_type = 0  # faiss.METRIC_INNER_PRODUCT
+        self._devices = None if devices is None else [int(x) for x in devices]
+        self._h = None
+        self._options: dict[str, int] = {}
+        if self.d != DIM:
+            raise RuntimeError(f"b2f supports d = {DIM} only (ConvDR hard-codes IndexFlatIP(768)), got {d}")
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def _ensure(self):
+        if self._h is None:
+            lib = _lib.load()
+            h = C.c_void_p()
+            if self._devices:
+                arr = (C.c_int * len(self._devices))(*self._devices)
+                _lib.check(lib.b2f_create(self.d, arr, len(self._devices), C.byref(h)))
+            else:
+                _lib.check(lib.b2f_create(self.d, None, 0, C.byref(h)))
+            self._h = h
+            for k, v in self._options.items():
+                _lib.check(lib.b2f_set_option(self._h, k.encode(), int(v)))
+        return self._h
+
+    def close(self) -> None:
+        if self._h is not None:
+            _lib.load().b2f_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- faiss surface --------------------------------------------------------------------------
+    @property
+    def ntotal(self) -> int:
+        if self._h is None:
+            return 0
+        return int(_lib.load().b2f_ntotal(self._h))
+
+    def _as_rows(self, x, what: str) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.ndim == 2, f"{what} must be a 2-d array, got shape {x.shape}"
+        assert x.shape[1] == self.d, f"{what} has dimension {x.shape[1]}, index has {self.d}"
+        return x
+
+    def add(self, x) -> None:
+        """index.add(x): append rows; ids are implicit, continuing from ntotal.  Copies x."""
+        x = self._as_rows(x, "x")
+        h = self._ensure()
+        _lib.check(_lib.load().b2f_add(h, x.ctypes.data, x.shape[0]))
+
+    def add_with_ids(self, x, ids) -> None:
+        """Append rows with explicit int64 labels (folds reference :190 `embedding2id[I]`)."""
+        x = self._as_rows(x, "x")
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        assert ids.shape == (x.shape[0],), "ids must have one label per row"
+        h = self._ensure()
+        _lib.check(_lib.load().b2f_add_with_ids(h, x.ctypes.data, ids.ctypes.data, x.shape[0]))
+
+    def search(self, x, k: int):
+        """D, I = index.search(x, k): exact top-k by inner product, sorted descending."""
+        x = self._as_rows(x, "x")
+        k = int(k)
+        assert k > 0, "k must be positive"
+        nq = x.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        h = self._ensure()
+        _lib.check(_lib.load().b2f_search(h, x.ctypes.data, nq, k, D.ctypes.data, I.ctypes.data))
+        return D, I
+
+    def reconstruct_n(self, i0: int, ni: int, shard: int = 0) -> np.ndarray:
+        """IndexFlat.reconstruct_n: stored rows [i0, i0+ni) of one shard, as float32 [ni, d]."""
+        out = np.empty((int(ni), self.d), dtype=np.float32)
+        _lib.check(_lib.load().b2f_reconstruct_n(self._ensure(), int(shard), int(i0), int(ni), out.ctypes.data))
+        return out
+
+    def reset(self) -> None:
+        """index.reset(): drop all rows (device buffers are kept for the next block by default)."""
+        if self._h is not None:
+            _lib.check(_lib.load().b2f_reset(self._h))
+
+    # -- device-resident extensions ("next" rows of SURVEY §8f) ----------------------------------
+    def reserve(self, n_per_shard: int) -> None:
+        _lib.check(_lib.load().b2f_reserve(self._ensure(), int(n_per_shard)))
+
+    def add_device(self, x, shard: int = 0) -> None:
+        """Append a CUDA float32 torch tensor [n, d] living on the shard's device (no host copy)."""
+        assert x.is_cuda and x.dtype.is_floating_point and x.dim() == 2 and x.shape[1] == self.d
+        import torch
+        x = x.contiguous().to(torch.float32)
+        _lib.check(_lib.load().b2f_add_device(self._ensure(), int(shard), x.data_ptr(), x.shape[0]))
+
+    def add_synthetic(self, n: int, *, first_row: int = 0, seed: int = 0, stream: int = 0, norm: float = 1.0,
+                      shard: int = 0, id_base: Optional[int] = None) -> None:
+        """Append rows [first_row, first_row+n) of the synthetic stream (seed, stream); see synth.py."""
+        if id_base is None:
+            id_base = first_row
+        _lib.check(_lib.load().b2f_add_synthetic(self._ensure(), int(shard), int(first_row), int(n), int(seed),
+                                                 int(stream), float(norm), int(id_base)))
+
+    def search_device(self, q, k: int):
+        """Search with a CUDA torch tensor of queries; returns CUDA tensors (D, I).  Single shard."""
+        import torch
+        assert q.is_cuda and q.dim() == 2 and q.shape[1] == self.d
+        q = q.contiguous().to(torch.float32)
+        nq = q.shape[0]
+        D = torch.empty((nq, int(k)), dtype=torch.float32, device=q.device)
+        I = torch.empty((nq, int(k)), dtype=torch.int64, device=q.device)
+        _lib.check(_lib.load().b2f_search_device(self._ensure(), q.data_ptr(), nq, int(k), D.data_ptr(),
+                                                 I.data_ptr()))
+        return D, I
+
+    def search_device_into(self, q, k: int, D, I) -> None:
+        """Same, into caller-provided CUDA tensors (no allocation inside a timed loop)."""
+        _lib.check(_lib.load().b2f_search_device(self._ensure(), q.data_ptr(), q.shape[0], int(k), D.data_ptr(),
+                                                 I.data_ptr()))
+
+    def merge_device(self, D_parts, I_parts):
+        """Merge per-shard results [G, nq, k] (CUDA tensors on this index's device) into [nq, k]."""
+        import torch
+        G, nq, k = D_parts.shape
+        D = torch.empty((nq, k), dtype=torch.float32, device=D_parts.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=D_parts.device)
+        _lib.check(_lib.load().b2f_merge_device(self._ensure(), D_parts.data_ptr(), I_parts.data_ptr(), int(G),
+                                                int(nq), int(k), D.data_ptr(), I.data_ptr()))
+        return D, I
+
+    # -- knobs / introspection --------------------------------------------------------------------
+    def set_option(self, key: str, value) -> None:
+        if key == "path" and isinstance(value, str):
+            value = PATHS[value]
+        self._options[key] = int(value)
+        if self._h is not None:
+            _lib.check(_lib.load().b2f_set_option(self._h, key.encode(), int(value)))
+
+    def stat(self, key: str) -> float:
+        out = C.c_double()
+        _lib.check(_lib.load().b2f_get_stat(self._ensure(), key.encode(), C.byref(out)))
+        return float(out.value)
+
+    def stream_ptr(self, shard: int = 0) -> int:
+        return int(_lib.load().b2f_stream(self._ensure(), int(shard)) or 0)
+
+    @property
+    def num_shards(self) -> int:
+        return int(_lib.load().b2f_num_shards(self._ensure()))
+
+    def shard_rows(self, shard: int) -> int:
+        return int(_lib.load().b2f_shard_rows(self._ensure(), int(shard)))

@@ -1,0 +1,149 @@
+/*
+ * b2f.h — C ABI of the B200-native exact inner-product top-k engine ("b2f" = B200 flat).
+ *
+ * This is the drop-in boundary for the dense-retrieval hot path of thunlp/ConvDR:
+ * the faiss.IndexFlatIP add / search / reset calls made by
+ *   drivers/run_convdr_inference.py::search_one_by_one   (reference :157-242)
+ * and the index construction in main()                   (reference :327-370).
+ *
+ * The reference has no FFI of its own — it binds FAISS through SWIG — so every
+ * entry point below cites the FAISS-Python call site in the reference that it
+ * replaces.  The Python facade (convdr_b200/faiss_compat.py) binds these with
+ * ctypes; INTEGRATION.md shows the stub a ConvDR maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary;
+ *   - every function returns 0 on success, a B2F_ERR_* code otherwise, and never
+ *     throws; b2f_last_error() returns a thread-local description;
+ *   - "host" pointers are ordinary (pageable or pinned) host memory, "dev"
+ *     pointers are CUDA device memory on the index's (first) device;
+ *   - vectors are row-major float32 [n, d], d fixed at 768 (reference :353);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with B2F_ERR_NO_DEVICE.
+ */
+#ifndef B2F_H_
+#define B2F_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2F_DIM 768 /* reference drivers/run_convdr_inference.py:353 hard-codes 768 */
+#define B2F_MAX_K 2048 /* FAISS-GPU's own limit; reference uses 100 (:316-319) and 1000 */
+
+enum {
+  B2F_OK = 0,
+  B2F_ERR_INVALID = 1,   /* bad argument (dimension, k, null pointer, ...) */
+  B2F_ERR_NO_DEVICE = 2, /* no usable CUDA device / driver */
+  B2F_ERR_CUDA = 3,      /* a CUDA runtime / driver call failed */
+  B2F_ERR_OOM = 4,       /* device allocation failed */
+  B2F_ERR_INTERNAL = 5   /* selection pipeline failed to converge (a bug) */
+};
+
+typedef struct b2f_index b2f_index;
+
+/* Scoring engines (b2f_set_option "path"). AUTO picks by batch size. */
+enum {
+  B2F_PATH_AUTO = 0,
+  B2F_PATH_SCAN_F32 = 1,   /* fp32 128-bit loads + warp-shuffle dots (small batches)   */
+  B2F_PATH_SCAN_EXACT = 2, /* same scan, fp64 accumulation, total-order keys (robust fallback) */
+  B2F_PATH_UMMA_BF16 = 3   /* TMA + tcgen05/TMEM bf16 prefilter, exact rescoring        */
+};
+
+/* faiss.get_num_gpus()                                  reference :327 */
+int b2f_device_count(void);
+
+/* faiss.IndexFlatIP(768) [+ index_cpu_to_gpu_multiple(vres, vdev, cpu_index, co)
+ * with co.shard = True]                                 reference :353, :355-368
+ * devices == NULL or n_dev == 0 -> device 0 only.  With n_dev > 1 each add() is
+ * split in n_dev contiguous chunks (FAISS IndexShards, successive ids).        */
+int b2f_create(int d, const int* devices, int n_dev, b2f_index** out);
+
+/* index.add(passage_embedding)                          reference :180
+ * Copies x (the driver deletes its array right after, :203-204); ids are
+ * implicit and continue from ntotal.                                          */
+int b2f_add(b2f_index* idx, const float* x_host, int64_t n);
+
+/* Same, with explicit int64 labels returned by search instead of positions —
+ * folds `passage_embedding2id[I]` (reference :190) into the engine.           */
+int b2f_add_with_ids(b2f_index* idx, const float* x_host, const int64_t* ids_host, int64_t n);
+
+/* Zero-copy variant: x_dev is device memory on shard `shard`'s device.         */
+int b2f_add_device(b2f_index* idx, int shard, const float* x_dev, int64_t n);
+
+/* Pre-size every shard for `n_per_shard` rows (avoids regrowth copies).        */
+int b2f_reserve(b2f_index* idx, int64_t n_per_shard);
+
+/* Append n synthetic rows generated on device: counter-based Philox4x32-10,
+ * integer Irwin-Hall components, exact L2 normalisation, times `norm`.
+ * Row r of stream (seed, stream) is bit-identical to convdr_b200/synth.py and
+ * oracle/synth.c, so CPU checks can regenerate any row.  Rows
+ * [first_row, first_row+n) are appended to shard `shard`; their ids are
+ * id_base .. id_base+n-1.                                                      */
+int b2f_add_synthetic(b2f_index* idx, int shard, int64_t first_row, int64_t n, uint64_t seed,
+                      uint64_t stream, float norm, int64_t id_base);
+
+/* D, I = index.search(query_embedding, topN)            reference :182
+ * q_host float32 [nq, d]; D float32 [nq, k] sorted descending; I int64 [nq, k];
+ * missing results (ntotal < k) are padded with D = -FLT_MAX, I = -1.
+ * Scores are the exactly-rounded fp32 value of the fp64 dot product; order is
+ * (score desc, insertion position asc).                                        */
+int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_host,
+               int64_t* I_host);
+
+/* Device-resident variant (single-shard indexes): q_dev / D_dev / I_dev live on
+ * the shard's device; work is enqueued on the index stream (b2f_stream) and the
+ * stream is synchronised before returning (the candidate-overflow flags are
+ * checked on the host).                                                        */
+int b2f_search_device(b2f_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
+                      int64_t* I_dev);
+
+/* Merge `n_parts` per-shard results [n_parts, nq, k] (device memory, each part
+ * sorted descending, padded with -FLT_MAX / -1) into the global top-k
+ * [nq, k] — the device-side replacement of the Python 2-way merge
+ * (reference :206-229) and of FAISS IndexShards' CPU merge.  Used after the
+ * NCCL all-gather in the one-process-per-GPU layout.                           */
+int b2f_merge_device(b2f_index* idx, const float* D_parts_dev, const int64_t* I_parts_dev,
+                     int n_parts, int64_t nq, int k, float* D_dev, int64_t* I_dev);
+
+/* faiss IndexFlat.reconstruct_n(i0, ni): copy stored rows [row0, row0+n) of shard
+ * `shard` (shard-local positions) back to host memory — inspection / tests.    */
+int b2f_reconstruct_n(b2f_index* idx, int shard, int64_t row0, int64_t n, float* out_host);
+
+/* index.reset()                                         reference :202 */
+int b2f_reset(b2f_index* idx);
+
+/* index.ntotal */
+int64_t b2f_ntotal(const b2f_index* idx);
+
+/* Rows on one shard / number of shards. */
+int64_t b2f_shard_rows(const b2f_index* idx, int shard);
+int b2f_num_shards(const b2f_index* idx);
+
+/* Raw CUDA stream (cudaStream_t) of shard `shard`, for event timing in bench.py. */
+void* b2f_stream(b2f_index* idx, int shard);
+
+/* Tuning knobs: "path" (B2F_PATH_*), "shadow" (keep the bf16 copy, default 1),
+ * "growth" (phase growth factor), "margin_ppm" (scale of the rigorous error
+ * margin in parts-per-million, default 1000000), "keep_on_reset" (default 1),
+ * "scan_max_auto" (largest batch AUTO sends to the SIMT scan, default 4).      */
+int b2f_set_option(b2f_index* idx, const char* key, int64_t value);
+
+/* Counters of the last search: "launches", "phases", "candidates",
+ * "fallback_queries", "path", "passes".                                        */
+int b2f_get_stat(const b2f_index* idx, const char* key, double* out);
+
+void b2f_destroy(b2f_index* idx);
+
+/* Thread-local description of the last error in this thread. */
+const char* b2f_last_error(void);
+
+/* Library build identification ("b2f <version> sm_100a"). */
+const char* b2f_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2F_H_ */
