@@ -122,6 +122,28 @@ struct Workspace {
   void* pin = nullptr;
 };
 
+struct Stats {
+  double launches = 0, phases = 0, candidates = 0, fallback_queries = 0, path = 0, passes = 0;
+  double score_ms = 0, score_launches = 0, score_rows = 0, select_ms = 0;
+};
+
+// Optional per-launch device timing ("profile" option): CUDA events on the shard stream around
+// every scoring launch (kind 0) and every refresh/final launch (kind 1).
+struct Prof {
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Span { int kind; size_t b, e; };
+  std::vector<Span> spans;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t ev;
+      cudaEventCreate(&ev);
+      pool.push_back(ev);
+    }
+    return pool[used++];
+  }
+};
+
 struct Shard {
   int dev = 0;
   cudaStream_t stream = nullptr;
@@ -138,10 +160,7 @@ struct Shard {
   Seg* segs_d = nullptr;
   int segs_d_cap = 0;
   Workspace ws;
-};
-
-struct Stats {
-  double launches = 0, phases = 0, candidates = 0, fallback_queries = 0, path = 0, passes = 0;
+  Prof prof;
 };
 
 }  // namespace
@@ -157,6 +176,7 @@ struct b2f_index {
   int64_t margin_ppm = 1000000;
   int keep_on_reset = 1;
   int scan_max_auto = 4;  // AUTO: batches up to this size use the SIMT scan
+  int profile = 0;
   Stats stats;
 };
 
@@ -321,6 +341,34 @@ __global__ void fill_pad_kernel(float* D, int64_t* I, int64_t n) {
   if (i < n) { D[i] = -FLT_MAX; I[i] = -1; }
 }
 
+struct ProfScope {
+  Prof* p;
+  cudaStream_t s;
+  size_t b = 0;
+  int kind;
+  ProfScope(b2f_index* idx, Shard& S, int kind_) : p(idx->profile ? &S.prof : nullptr), s(S.stream), kind(kind_) {
+    if (p) { b = p->used; cudaEventRecord(p->get(), s); }
+  }
+  ~ProfScope() {
+    if (p) { size_t e = p->used; cudaEventRecord(p->get(), s); p->spans.push_back({kind, b, e}); }
+  }
+};
+
+void collect_prof(b2f_index* idx, Shard& S) {
+  Prof& P = S.prof;
+  for (const Prof::Span& sp : P.spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, P.pool[sp.b], P.pool[sp.e]) == cudaSuccess) {
+      if (sp.kind == 0) { idx->stats.score_ms += ms; idx->stats.score_launches += 1; }
+      else idx->stats.select_ms += ms;
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  P.spans.clear();
+  P.used = 0;
+}
+
 // Rigorous worst-case error of a score computed from rounded operands / in reduced precision,
 // relative to ||q|| * ||p|| (Cauchy-Schwarz on sum |q_t p_t|):
 //   bf16 engine: two round-to-nearest bf16 operands (2 * 2^-9 + 2^-18) + fp32 accumulation of 768
@@ -402,7 +450,11 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       a.dense = dense ? 1 : 0; a.dense_row0 = 0; a.cand = W.cand[cur]; a.cnt = W.cnt; a.C = C;
       a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
       const int pairs = std::min(S.max_pairs, te - tb);
-      umma_score_select_kernel<<<2 * pairs, kUmmaThreads, smem, s>>>(tmap_p, tmap_q, a);
+      {
+        ProfScope ps(idx, S, 0);
+        umma_score_select_kernel<<<2 * pairs, kUmmaThreads, smem, s>>>(tmap_p, tmap_q, a);
+      }
+      st.score_rows += static_cast<double>(std::min<int64_t>(N, static_cast<int64_t>(te) * kTileRows) - begin);
       if (dense) n_override = (te - tb) * kTileRows;
     } else {
       ScanArgs a;
@@ -412,13 +464,20 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       const int64_t groups = (end - begin + kScanRows - 1) / kScanRows;
       const int blocks = static_cast<int>(std::min<int64_t>((groups + 7) / 8, static_cast<int64_t>(S.sm_count)));
       const size_t sm = scan_smem_bytes(nqp, plan.exact);
-      if (plan.exact) scan_kernel<true><<<std::max(blocks, 1), kScanThreads, sm, s>>>(a);
-      else scan_kernel<false><<<std::max(blocks, 1), kScanThreads, sm, s>>>(a);
+      {
+        ProfScope ps(idx, S, 0);
+        if (plan.exact) scan_kernel<true><<<std::max(blocks, 1), kScanThreads, sm, s>>>(a);
+        else scan_kernel<false><<<std::max(blocks, 1), kScanThreads, sm, s>>>(a);
+      }
+      st.score_rows += static_cast<double>(end - begin);
       if (dense) n_override = static_cast<int>(end - begin);
     }
     CU_TRY(cudaGetLastError());
-    refresh_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.cnt, C, k, plan.exact ? 1 : 0,
-                                              W.margin, W.tau, W.tauP, n_override);
+    {
+      ProfScope ps(idx, S, 1);
+      refresh_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.cnt, C, k, plan.exact ? 1 : 0,
+                                                W.margin, W.tau, W.tauP, n_override);
+    }
     CU_TRY(cudaGetLastError());
     cur ^= 1;
     st.launches += 2;
@@ -426,9 +485,12 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     begin = end;
     ++phase;
   }
-  final_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.cnt, C, k, plan.exact ? 0 : 1, q32p,
-                                          S.x32, S.segs_d, static_cast<int>(S.segs.size()),
-                                          S.has_ids ? S.idmap : nullptr, D_out, I_out, out_stride);
+  {
+    ProfScope ps(idx, S, 1);
+    final_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.cnt, C, k, plan.exact ? 0 : 1, q32p,
+                                            S.x32, S.segs_d, static_cast<int>(S.segs.size()),
+                                            S.has_ids ? S.idmap : nullptr, D_out, I_out, out_stride);
+  }
   CU_TRY(cudaGetLastError());
   st.launches += 1;
   st.passes += 1;
@@ -495,6 +557,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
 int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d) {
   CU_TRY(cudaSetDevice(S.dev));
   CU_TRY(cudaStreamSynchronize(S.stream));
+  if (idx->profile) collect_prof(idx, S);
   if (S.n == 0) return B2F_OK;
   Workspace& W = S.ws;
   std::vector<int64_t> bad;
@@ -524,6 +587,7 @@ int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k,
     }
   }
   CU_TRY(cudaStreamSynchronize(s));
+  if (idx->profile) collect_prof(idx, S);
   return B2F_OK;
 }
 
@@ -621,6 +685,7 @@ void b2f_destroy(b2f_index* idx) {
     dev_free(W.fbq); dev_free(W.fbD); dev_free(W.fbI);
     if (W.ovf_host) cudaFreeHost(W.ovf_host);
     if (W.pin) cudaFreeHost(W.pin);
+    for (cudaEvent_t ev : S.prof.pool) cudaEventDestroy(ev);
     if (S.ev) cudaEventDestroy(S.ev);
     if (S.stream) cudaStreamDestroy(S.stream);
   }
@@ -866,6 +931,8 @@ int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
     idx->margin_ppm = value;
   } else if (k == "keep_on_reset") {
     idx->keep_on_reset = value ? 1 : 0;
+  } else if (k == "profile") {
+    idx->profile = value ? 1 : 0;
   } else if (k == "scan_max_auto") {
     if (value < 0 || value > kScanMaxQ) return fail(B2F_ERR_INVALID, "scan_max_auto must be in [0, 32]");
     idx->scan_max_auto = static_cast<int>(value);
@@ -885,6 +952,10 @@ int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
   else if (k == "fallback_queries") *out = s.fallback_queries;
   else if (k == "path") *out = s.path;
   else if (k == "passes") *out = s.passes;
+  else if (k == "score_ms") *out = s.score_ms;
+  else if (k == "score_launches") *out = s.score_launches;
+  else if (k == "score_rows") *out = s.score_rows;
+  else if (k == "select_ms") *out = s.select_ms;
   else return fail(B2F_ERR_INVALID, "unknown stat '" + k + "'");
   return B2F_OK;
 }

@@ -72,8 +72,9 @@ class ShardedFlatIP:
         if self._Dg is None or self._Dg.shape != (self.world, nq, k) or self._Dg.device != D.device:
             self._Dg = torch.empty((self.world, nq, k), dtype=torch.float32, device=D.device)
             self._Ig = torch.empty((self.world, nq, k), dtype=torch.int64, device=D.device)
-        dist.all_gather_into_tensor(self._Dg, D.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(self._Ig, I.contiguous(), group=self.group)
+        # concatenated-along-dim-0 form: accepted by both NCCL and gloo
+        dist.all_gather_into_tensor(self._Dg.view(self.world * nq, k), D.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(self._Ig.view(self.world * nq, k), I.contiguous(), group=self.group)
         if D.is_cuda:
             torch.cuda.current_stream(D.device).synchronize()  # the merge runs on the engine's stream
         return self._merge(self._Dg, self._Ig)

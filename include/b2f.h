@@ -128,11 +128,14 @@ void* b2f_stream(b2f_index* idx, int shard);
 /* Tuning knobs: "path" (B2F_PATH_*), "shadow" (keep the bf16 copy, default 1),
  * "growth" (phase growth factor), "margin_ppm" (scale of the rigorous error
  * margin in parts-per-million, default 1000000), "keep_on_reset" (default 1),
- * "scan_max_auto" (largest batch AUTO sends to the SIMT scan, default 4).      */
+ * "scan_max_auto" (largest batch AUTO sends to the SIMT scan, default 4),
+ * "profile" (1: CUDA events around every scoring / selection launch).          */
 int b2f_set_option(b2f_index* idx, const char* key, int64_t value);
 
 /* Counters of the last search: "launches", "phases", "candidates",
- * "fallback_queries", "path", "passes".                                        */
+ * "fallback_queries", "path", "passes"; with "profile" on also "score_ms",
+ * "score_launches", "score_rows" (scoring kernels: device time, launches, rows
+ * streamed) and "select_ms" (refresh + final kernels).                         */
 int b2f_get_stat(const b2f_index* idx, const char* key, double* out);
 
 void b2f_destroy(b2f_index* idx);

@@ -46,19 +46,44 @@ def _gemm_f32(a: np.ndarray, b: np.ndarray, backend: str) -> np.ndarray:
     return a @ b.T
 
 
-def _topk_merge(best_s, best_i, s_blk, i0, k):
+def _block_topk(s_blk: np.ndarray, k: int, backend: str = "numpy"):
+    """Per-row top-k of one score block with the oracle's tie rule (score desc, index asc).
+    Fast path: argpartition; rows whose k-th value is tied with excluded entries are redone with a
+    full stable sort (argpartition picks arbitrarily among equal values)."""
+    nq, nb = s_blk.shape
+    if nb <= k:
+        order = np.argsort(-s_blk, axis=1, kind="stable")
+        return np.take_along_axis(s_blk, order, axis=1), order.astype(np.int64)
+    if backend == "torch":
+        import torch
+        tv, ti = torch.topk(torch.from_numpy(s_blk), k, dim=1, sorted=False)
+        vals, part = tv.numpy(), ti.numpy()
+    else:
+        part = np.argpartition(-s_blk, k - 1, axis=1)[:, :k]
+        vals = np.take_along_axis(s_blk, part, axis=1)
+    thr = vals.min(axis=1, keepdims=True)
+    tied_rows = np.nonzero((s_blk == thr).sum(axis=1) != (vals == thr).sum(axis=1))[0]
+    order = np.lexsort((part, -vals), axis=1)          # score desc, then index asc
+    vals = np.take_along_axis(vals, order, axis=1)
+    part = np.take_along_axis(part, order, axis=1)
+    for r in tied_rows:
+        o = np.argsort(-s_blk[r], kind="stable")[:k]
+        vals[r], part[r] = s_blk[r, o], o
+    return vals, part.astype(np.int64)
+
+
+def _topk_merge(best_s, best_i, s_blk, i0, k, backend: str = "numpy"):
     """Fold one score block [nq, nb] (db indices i0..i0+nb-1) into the running top-k.
     Order: score desc, index asc — equivalent to the strict-`>` heap at the k-th boundary."""
-    nq, nb = s_blk.shape
-    ids = np.broadcast_to(np.arange(i0, i0 + nb, dtype=np.int64), (nq, nb))
+    blk_s, blk_i = _block_topk(s_blk, k, backend)
+    blk_i = blk_i + i0
     if best_s is None:
-        cat_s, cat_i = s_blk, ids
-    else:
-        cat_s = np.concatenate([best_s, s_blk], axis=1)
-        cat_i = np.concatenate([best_i, ids], axis=1)
+        return blk_s, blk_i
+    cat_s = np.concatenate([best_s, blk_s], axis=1)
+    cat_i = np.concatenate([best_i, blk_i], axis=1)
     kk = min(k, cat_s.shape[1])
-    # indices in each row are already ascending left-to-right, so a stable sort on -score keeps
-    # the lower index first among equal scores
+    # earlier blocks hold lower indices and come first, so a stable sort on -score keeps the
+    # lower index first among equal scores
     order = np.argsort(-cat_s, axis=1, kind="stable")[:, :kk]
     return np.take_along_axis(cat_s, order, axis=1), np.take_along_axis(cat_i, order, axis=1)
 
@@ -80,7 +105,7 @@ def knn_inner_product(x: np.ndarray, xb: np.ndarray, k: int, backend: str = "num
         for j0 in range(0, n, bs_db):
             j1 = min(n, j0 + bs_db)
             s_blk = _gemm_f32(x[q0:q1], xb[j0:j1], backend)
-            best_s, best_i = _topk_merge(best_s, best_i, s_blk, j0, k)
+            best_s, best_i = _topk_merge(best_s, best_i, s_blk, j0, k, backend)
         kk = best_s.shape[1]
         D[q0:q1, :kk] = best_s
         I[q0:q1, :kk] = best_i

@@ -1,0 +1,315 @@
+"""GPU parity tests (run on a B200 with `-m gpu`): the CUDA path, called through the C ABI /
+faiss facade, against the oracle (FAISS-restated fp32 and fp64 truth) on the same seeded inputs.
+
+Bar (BASELINE.json north_star): ids identical to the reference except at ties within 1e-5 relative
+score; scores within 1e-5 relative.  The engine actually reports the correctly rounded fp64 dot, so
+against the fp64 truth we additionally require 1e-6.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import convdr_b200.faiss_compat as faiss
+from convdr_b200 import FlatIPIndex, driver, synth
+from oracle import c_oracle, flat_ip
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATHS = ["scan_f32", "scan_exact", "umma_bf16"]
+RTOL = 1e-5          # the tolerance north_star states
+RTOL_TRUTH = 1e-6    # what the exact rescoring actually delivers vs float64
+
+
+def make_index(path, P=None, devices=None, **opts):
+    idx = FlatIPIndex(768, devices=devices)
+    idx.set_option("path", path)
+    for k, v in opts.items():
+        idx.set_option(k, v)
+    if P is not None:
+        idx.add(P)
+    return idx
+
+
+def check_against_oracle(D, I, P, Q, k, also_fp32_oracle=True):
+    Dt, It = flat_ip.truth_fp64(Q, P, k)
+    score_of = lambda qi, ids: Q[qi].astype(np.float64) @ P[ids].astype(np.float64).T
+    r = flat_ip.compare(D, I, Dt, It, score_of, rtol=RTOL)
+    assert r["violations"] == 0, r
+    valid = It >= 0
+    rel = np.abs(D[valid].astype(np.float64) - Dt[valid]) / np.maximum(np.abs(Dt[valid]), 1e-30)
+    assert rel.max() <= RTOL_TRUTH, rel.max()
+    assert (np.diff(D, axis=1) <= 0).all(), "scores must be sorted descending"
+    if also_fp32_oracle:
+        Do, Io = flat_ip.knn_inner_product(Q, P, k)
+        r2 = flat_ip.compare(D, I, Do, Io, score_of, rtol=RTOL)
+        assert r2["violations"] == 0, r2
+    return r
+
+
+@pytest.fixture(scope="module")
+def c1_data():
+    # BASELINE config 1: 100k x 768, 173 queries
+    return c_oracle.synth_block(0, 100000), c_oracle.synth_block(0, 173, stream=1)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_config1_100k_173q_top100(path, c1_data):
+    P, Q = c1_data
+    idx = make_index(path, P)
+    assert idx.ntotal == 100000
+    D, I = idx.search(Q, 100)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (173, 100)
+    r = check_against_oracle(D, I, P, Q, 100)
+    assert r["exact_rows"] >= 170
+    assert idx.stat("fallback_queries") == 0
+    assert int(idx.stat("path")) == {"scan_f32": 1, "scan_exact": 2, "umma_bf16": 3}[path]
+    assert idx.stat("launches") > 0
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_results_are_bitwise_path_independent(path, c1_data):
+    P, Q = c1_data
+    ref = make_index("scan_exact", P[:30000])
+    D0, I0 = ref.search(Q[:40], 50)
+    idx = make_index(path, P[:30000])
+    D, I = idx.search(Q[:40], 50)
+    np.testing.assert_array_equal(I, I0)
+    np.testing.assert_array_equal(D, D0)
+
+
+@pytest.mark.parametrize("path", ["scan_f32", "umma_bf16"])
+def test_top1000_selection_pressure(path, c1_data):
+    P, Q = c1_data  # BASELINE config 2's k = 1000 (gen_ranking_data.py negatives), reduced rows
+    idx = make_index(path, P)
+    D, I = idx.search(Q[:64], 1000)
+    check_against_oracle(D, I, P, Q[:64], 1000, also_fp32_oracle=False)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("n", [1, 3, 100, 255, 256, 257, 4095, 18943, 18944, 18945, 40001])
+def test_ragged_collection_sizes(path, n, c1_data):
+    P, Q = c1_data
+    idx = make_index(path, P[:n])
+    k = 10
+    D, I = idx.search(Q[:21], k)
+    if n < k:
+        assert (I[:, n:] == -1).all() and (D[:, n:] == -np.float32(3.4028234663852886e38)).all()
+    check_against_oracle(D, I, P[:n], Q[:21], k)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("nq", [1, 2, 5, 16, 17, 33, 191, 192, 193, 400])
+def test_ragged_query_batches(path, nq):
+    P = c_oracle.synth_block(0, 20000, seed=3)
+    Q = c_oracle.synth_block(0, nq, seed=3, stream=1)
+    idx = make_index(path, P)
+    D, I = idx.search(Q, 20)
+    check_against_oracle(D, I, P, Q, 20)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_empty_index_and_k_larger_than_ntotal(path):
+    Q = c_oracle.synth_block(0, 5, stream=1)
+    idx = make_index(path)
+    D, I = idx.search(Q, 4)
+    assert (I == -1).all() and (D == -np.float32(3.4028234663852886e38)).all()
+    P = c_oracle.synth_block(0, 7)
+    idx.add(P)
+    D, I = idx.search(Q, 12)
+    assert (I[:, 7:] == -1).all()
+    assert sorted(I[0, :7].tolist()) == list(range(7))
+    check_against_oracle(D, I, P, Q, 12)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_two_adds_equal_one_add_and_reset_readd(path):
+    P = c_oracle.synth_block(0, 30000, seed=5)
+    Q = c_oracle.synth_block(0, 23, seed=5, stream=1)
+    a = make_index(path, P)
+    b = make_index(path)
+    b.add(P[:11111])
+    b.add(P[11111:])
+    assert a.ntotal == b.ntotal == 30000
+    Da, Ia = a.search(Q, 30)
+    Db, Ib = b.search(Q, 30)
+    np.testing.assert_array_equal(Ia, Ib)
+    np.testing.assert_array_equal(Da, Db)
+    b.reset()
+    assert b.ntotal == 0
+    b.add(P[20000:])
+    D, I = b.search(Q, 30)
+    check_against_oracle(D, I, P[20000:], Q, 30)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_known_answers_identity_and_planted(path):
+    P = np.zeros((300, 768), dtype=np.float32)
+    P[np.arange(300), np.arange(300)] = 1.0
+    Q = np.zeros((2, 768), dtype=np.float32)
+    Q[0, 5], Q[0, 7] = 2.0, 1.0
+    Q[1, 299], Q[1, 0] = 1.0, 0.5
+    D, I = make_index(path, P).search(Q, 3)
+    assert I[0, :2].tolist() == [5, 7] and D[0, :2].tolist() == [2.0, 1.0]
+    assert I[1, :2].tolist() == [299, 0] and D[1, :2].tolist() == [1.0, 0.5]
+    assert D[0, 2] == 0.0 and I[0, 2] == 0   # remaining scores tie at 0 -> lowest index (our total order)
+    P = c_oracle.synth_block(0, 50000, seed=1)
+    q = c_oracle.synth_block(0, 1, seed=1, stream=1)
+    plant = {17: 3.0, 41500: 2.5, 999: 2.0, 4: 1.5}
+    for row, s in plant.items():
+        P[row] = q[0] * np.float32(s)
+    D, I = make_index(path, P).search(q, 4)
+    assert I[0].tolist() == [17, 41500, 999, 4]
+    np.testing.assert_allclose(D[0], [3.0, 2.5, 2.0, 1.5], rtol=1e-6)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_all_equal_scores_use_the_total_order(path):
+    """Every row identical: all scores tie.  Candidate lists overflow on the filtering engines and
+    the exact engine must finish the query (lowest positions win)."""
+    row = c_oracle.synth_block(0, 1, seed=2)
+    P = np.tile(row, (60000, 1))
+    Q = c_oracle.synth_block(0, 3, seed=2, stream=1)
+    idx = make_index(path, P)
+    D, I = idx.search(Q, 25)
+    assert I.tolist() == [list(range(25))] * 3
+    if path != "scan_exact":
+        assert idx.stat("fallback_queries") == 3
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_non_unit_norm_rows_scale_28(path):
+    P = c_oracle.synth_block(0, 40000, seed=4, norm=28.0)   # real ANCE scale
+    Q = c_oracle.synth_block(0, 19, seed=4, stream=1, norm=28.0)
+    D, I = make_index(path, P).search(Q, 50)
+    check_against_oracle(D, I, P, Q, 50)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_duplicate_rows_exact_ties_inside_topk(path):
+    P = c_oracle.synth_block(0, 30000, seed=6)
+    Q = c_oracle.synth_block(0, 8, seed=6, stream=1)
+    _, I0 = flat_ip.knn_inner_product(Q, P, 5)
+    P[29000:29005] = P[I0[0, :5]]         # exact copies of query 0's top-5, at higher positions
+    D, I = make_index(path, P).search(Q, 12)
+    Dt, It = flat_ip.truth_fp64(Q, P, 12)
+    np.testing.assert_array_equal(I, It)   # (score desc, position asc) is also the truth's order
+    assert I[0, 0] < 29000 and I[0, 1] >= 29000 and D[0, 0] == D[0, 1]
+
+
+def test_add_with_ids_folds_offset_translation():
+    P = c_oracle.synth_block(0, 25000, seed=8)
+    Q = c_oracle.synth_block(0, 11, seed=8, stream=1)
+    ids = (np.arange(25000, dtype=np.int64) * 8 + 3)[::-1].copy()   # strided offsets like block files
+    idx = make_index("auto")
+    idx.add_with_ids(P, ids)
+    D, I = idx.search(Q, 20)
+    Do, Io = flat_ip.truth_fp64(Q, P, 20)
+    np.testing.assert_array_equal(I, ids[Io])
+    np.testing.assert_allclose(D, Do, rtol=RTOL_TRUTH)
+    with pytest.raises(RuntimeError):
+        idx.add(P[:10])
+
+
+def test_reconstruct_and_device_synthetic_rows_are_bit_identical_to_host():
+    idx = make_index("auto")
+    idx.add_synthetic(5000, first_row=123456789012, seed=9, stream=4, norm=3.5)
+    got = idx.reconstruct_n(0, 5000)
+    want = synth.block(123456789012, 5000, seed=9, stream=4, norm=3.5)
+    np.testing.assert_array_equal(got, want)
+    Q = c_oracle.synth_block(0, 6, seed=9, stream=1)
+    D, I = idx.search(Q, 10)
+    Do, Io = flat_ip.truth_fp64(Q, want, 10)
+    np.testing.assert_array_equal(I, Io + 123456789012)
+
+
+@pytest.mark.parametrize("name", ["three_blocks", "one_block", "eight_blocks_k100",
+                                  "short_block_wraps_minus_one", "ties_across_blocks"])
+def test_driver_search_one_by_one_on_gpu_matches_reference_golden(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "search_one_by_one.npz"))
+    Dg, Ig = z[name + "/D"], z[name + "/I"]
+    n, W, nq, topN, dup = (int(v) for v in z[name + "/params"])
+    P = synth.block(0, n, seed=7, stream=0)
+    if dup:
+        P[n - dup:] = P[:dup]
+    Q = synth.block(0, nq, seed=7, stream=1)
+    with tempfile.TemporaryDirectory() as tmp:
+        for r in range(W):
+            ids = np.arange(r, n, W, dtype=np.int64)
+            flat_ip.write_block(tmp, r, P[ids], ids)
+        index = faiss.IndexFlatIP(768)                       # the driver's no --use_gpu path (:369-370)
+        D, I = driver.search_one_by_one(tmp, index, Q, topN, verbose=False)
+        index2 = faiss.IndexFlatIP(768)
+        Dr, Ir = driver.search_resident(tmp, index2, Q, topN)
+    assert D.shape == Dg.shape and D.dtype == np.float64 and I.dtype == np.int64
+    pad = Dg < -1e38
+    np.testing.assert_array_equal(pad, D < -1e38)
+    np.testing.assert_array_equal(I[pad], Ig[pad])           # -1 wrapped to the block's last offset, like the reference
+    score_of = lambda qi, ids: Q[qi].astype(np.float64) @ P[ids].astype(np.float64).T
+    Dc, Dgc = np.where(pad, -1.0, D), np.where(pad, -1.0, Dg)
+    r = flat_ip.compare(Dc, I, Dgc, Ig, score_of, rtol=RTOL)
+    assert r["violations"] == 0, r
+    if name != "ties_across_blocks":
+        assert r["exact_rows"] == nq, r                      # small cases: no near-ties, ids identical
+    if name != "short_block_wraps_minus_one":
+        r2 = flat_ip.compare(Dr, Ir, Dgc[:, :topN], Ig[:, :topN], score_of, rtol=RTOL)
+        assert r2["violations"] == 0, r2
+
+
+def test_multi_gpu_shards_in_one_process_match_single_gpu(gpu_count):
+    if gpu_count < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    P = c_oracle.synth_block(0, 60001, seed=10)
+    Q = c_oracle.synth_block(0, 50, seed=10, stream=1)
+    one = make_index("auto", P)
+    D1, I1 = one.search(Q, 40)
+    vres, vdev = faiss.GpuResourcesVector(), faiss.Int32Vector()
+    for i in range(gpu_count):
+        vdev.push_back(i)
+        vres.push_back(faiss.StandardGpuResources())
+    co = faiss.GpuMultipleClonerOptions()
+    co.shard = True
+    multi = faiss.index_cpu_to_gpu_multiple(vres, vdev, faiss.IndexFlatIP(768), co)
+    multi.add(P)
+    assert multi.num_shards == gpu_count and multi.ntotal == 60001
+    Dm, Im = multi.search(Q, 40)
+    np.testing.assert_array_equal(Im, I1)
+    np.testing.assert_array_equal(Dm, D1)
+
+
+def test_device_resident_search_and_merge_kernel():
+    import torch
+    P = c_oracle.synth_block(0, 30000, seed=12)
+    Q = c_oracle.synth_block(0, 33, seed=12, stream=1)
+    idx = make_index("auto", P)
+    Dh, Ih = idx.search(Q, 16)
+    qd = torch.from_numpy(Q).cuda()
+    Dd, Id = idx.search_device(qd, 16)
+    np.testing.assert_array_equal(Id.cpu().numpy(), Ih)
+    np.testing.assert_array_equal(Dd.cpu().numpy(), Dh)
+    # split the collection in 3 parts, search each, merge on device == search of the whole
+    parts = []
+    edges = [0, 9000, 21000, 30000]
+    for a, b in zip(edges[:-1], edges[1:]):
+        sub = make_index("auto")
+        sub.add_with_ids(P[a:b], np.arange(a, b, dtype=np.int64))
+        parts.append(sub.search_device(qd, 16))
+    Dp = torch.stack([p[0] for p in parts]).contiguous()
+    Ip = torch.stack([p[1] for p in parts]).contiguous()
+    Dm, Im = idx.merge_device(Dp, Ip)
+    np.testing.assert_array_equal(Im.cpu().numpy(), Ih)
+    np.testing.assert_array_equal(Dm.cpu().numpy(), Dh)
+
+
+def test_auto_policy_and_invalid_arguments():
+    P = c_oracle.synth_block(0, 20000, seed=13)
+    idx = make_index("auto", P)
+    idx.search(c_oracle.synth_block(0, 2, stream=1), 5)
+    assert int(idx.stat("path")) == 1            # tiny batch -> SIMT scan (fp32 128-bit loads)
+    idx.search(c_oracle.synth_block(0, 64, stream=1), 5)
+    assert int(idx.stat("path")) == 3            # dense contraction -> tcgen05
+    with pytest.raises(RuntimeError):
+        idx.search(c_oracle.synth_block(0, 2, stream=1), 4096)   # k beyond the supported maximum
+    with pytest.raises(AssertionError):
+        idx.search(np.zeros((2, 100), dtype=np.float32), 5)
