@@ -73,12 +73,14 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 row-major [rows, 768] tensor, box = 64 columns (128 bytes) x box_rows, 128-byte swizzle.
-int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint32_t box_rows) {
+// bf16 tensor [rows, cols] with row pitch cols*2 bytes, box = 64 columns (128 bytes) x box_rows,
+// 128-byte swizzle.  Queries: cols = 768 (row-major).  Shadow: cols = 64 — the K-block-major tiled
+// layout (common.cuh) is a [tiles*12*128, 64] matrix of 128-byte rows.
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint32_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(B2F_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kD), rows};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(kD) * 2};
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), rows};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -211,7 +213,7 @@ int ensure_capacity(b2f_index* idx, Shard& S, int64_t need) {
   int64_t* nid = nullptr;
   B2F_TRY(dev_alloc(&n32, static_cast<size_t>(ncap) * kD));
   if (idx->shadow) {
-    int rc = dev_alloc(&n16, static_cast<size_t>(ncap) * kD);
+    int rc = dev_alloc(&n16, static_cast<size_t>(shadow_rows_padded(ncap)) * kD);
     if (rc != B2F_OK) { dev_free(n32); return rc; }
   }
   if (S.has_ids) {
@@ -221,7 +223,8 @@ int ensure_capacity(b2f_index* idx, Shard& S, int64_t need) {
   if (S.n > 0) {
     CU_TRY(cudaMemcpyAsync(n32, S.x32, static_cast<size_t>(S.n) * kD * 4, cudaMemcpyDeviceToDevice, S.stream));
     if (n16 && S.x16)
-      CU_TRY(cudaMemcpyAsync(n16, S.x16, static_cast<size_t>(S.n) * kD * 2, cudaMemcpyDeviceToDevice, S.stream));
+      CU_TRY(cudaMemcpyAsync(n16, S.x16, static_cast<size_t>(shadow_rows_padded(S.n)) * kD * 2,
+                             cudaMemcpyDeviceToDevice, S.stream));  // tiles are stored in row order
     if (nid && S.idmap)
       CU_TRY(cudaMemcpyAsync(nid, S.idmap, static_cast<size_t>(S.n) * 8, cudaMemcpyDeviceToDevice, S.stream));
     CU_TRY(cudaStreamSynchronize(S.stream));
@@ -426,8 +429,9 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     n_cols = static_cast<int>(round_up(nqp, 16));
     stages = umma_stages(n_cols);
     smem = umma_smem_bytes(n_cols, stages);
-    B2F_TRY(make_tmap_bf16(&tmap_p, S.x16, static_cast<uint64_t>(N), kTileRowsCta));
-    B2F_TRY(make_tmap_bf16(&tmap_q, q16p, static_cast<uint64_t>(n_cols), static_cast<uint32_t>(n_cols / 2)));
+    B2F_TRY(make_tmap_bf16(&tmap_p, S.x16, static_cast<uint64_t>(shadow_rows_padded(N)) * kNumKBlocks, kBlockK,
+                           kTileRowsCta));
+    B2F_TRY(make_tmap_bf16(&tmap_q, q16p, static_cast<uint64_t>(n_cols), kD, static_cast<uint32_t>(n_cols / 2)));
   }
 
   // Phase boundaries in rows.  Dense phase first, then geometric growth (or, in exact mode,

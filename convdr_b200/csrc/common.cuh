@@ -11,6 +11,25 @@ constexpr int kRowF4 = kD / 4;     // float4 chunks per row (192)
 constexpr int kF4PerLane = kRowF4 / 32;  // 6 float4 per lane per row
 
 // ---------------------------------------------------------------------------------------------
+// Layout of the bf16 shadow copy streamed by the tensor engine: "K-block-major tiles".
+// Rows are grouped in tiles of 128; inside a tile the 12 K-blocks (64 columns = 128 bytes each)
+// are stored one after the other, each as 128 rows x 128 bytes.  One TMA stage (128 rows of one
+// K-block) is therefore ONE contiguous 16 KB read instead of 128 granules of 128 B strided by the
+// 1536-byte row pitch.  Element (row, col) lives at shadow_index(row, col) (in bf16 elements).
+// ---------------------------------------------------------------------------------------------
+constexpr int kShadowTileRows = 128;
+constexpr int kShadowKBlock = 64;
+__host__ __device__ __forceinline__ int64_t shadow_index(int64_t row, int col) {
+  const int64_t tile = row / kShadowTileRows;
+  const int r = static_cast<int>(row % kShadowTileRows);
+  const int kb = col / kShadowKBlock, c = col % kShadowKBlock;
+  return ((tile * (kD / kShadowKBlock) + kb) * kShadowTileRows + r) * kShadowKBlock + c;
+}
+__host__ __device__ __forceinline__ int64_t shadow_rows_padded(int64_t rows) {
+  return (rows + kShadowTileRows - 1) / kShadowTileRows * kShadowTileRows;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Candidate records.  A candidate is one 64-bit word:
 //   hi 32 bits: order-preserving key of the fp32 score (larger key <=> larger score)
 //   lo 32 bits: ~row  (so that, for equal scores, the LOWER row compares larger)

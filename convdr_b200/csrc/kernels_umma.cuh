@@ -85,8 +85,13 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Remote arrive on a barrier of the peer CTA.  Deliberately the plain form (default .release.cta):
+// `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR, which cost ~1300 cycles per TMA stage
+// when the peer's producer executed it (profiles/r01: the whole pipeline ran at that pace).  The
+// data these barriers guard travels through the async proxy (TMA complete_tx) or is ordered by
+// tcgen05.fence::before_thread_sync, not by this arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // Bounded wait: a protocol bug must end in a trap (reported as a CUDA error), never in a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
@@ -249,13 +254,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
                       static_cast<int>(cta_rank) * n_half, kHintEvictLast);
     uint32_t stage = 0, phase = 0;
     for (int tile = a.tile_begin + pair; tile < a.tile_end; tile += npairs) {
-      const int row0 = tile * kTileRows + static_cast<int>(cta_rank) * kTileRowsCta;
+      // shadow layout: CTA tile t = 2*tile + rank, K-block kb -> 128 consecutive 128-byte rows
+      const int blk0 = (tile * 2 + static_cast<int>(cta_rank)) * kNumKBlocks;
       for (int kb = 0; kb < kNumKBlocks; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1u, a.err);
         const uint32_t full_leader = mapa_u32(bar_full + 8 * stage, 0);
         if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2u * kStageBytes);
         else mbar_arrive_cluster(full_leader);
-        tma_load_2d_2sm(smem_a + stage * kStageBytes, &tmap_p, full_leader, kb * kBlockK, row0,
+        tma_load_2d_2sm(smem_a + stage * kStageBytes, &tmap_p, full_leader, 0, (blk0 + kb) * kTileRowsCta,
                         kHintEvictFirst);
         if (++stage == static_cast<uint32_t>(a.stages)) { stage = 0; phase ^= 1u; }
       }
@@ -317,23 +323,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
           for (int j = 0; j < 16; ++j)
             m |= (__uint_as_float(v[j]) >= tau_s[c0 + j]) ? (1u << j) : 0u;
           if (!row_ok) m = 0;
-          uint32_t any = __reduce_or_sync(0xffffffffu, m);
-          while (any) {  // rare: some row of this warp beat the threshold of query c0+j
-            const int j = __ffs(any) - 1;
-            any &= any - 1;
-            const int q = c0 + j;
-            const bool pass = (m >> j) & 1u;
-            const uint32_t b = __ballot_sync(0xffffffffu, pass);
-            const float s = __uint_as_float(tmem_ld_x1(taddr + c0 + j));
-            tmem_ld_wait();
-            const int lead = __ffs(b) - 1;
-            int slot0 = 0;
-            if (lane == lead) slot0 = atomicAdd(a.cnt + q, __popc(b));
-            slot0 = __shfl_sync(0xffffffffu, slot0, lead);
-            if (pass) {
-              const int slot = slot0 + __popc(b & lt_mask);
-              if (slot < a.C) a.cand[static_cast<int64_t>(q) * a.C + slot] = pack_cand(s, static_cast<uint32_t>(row));
-              else a.ovf[q] = 1;
+          const uint32_t any = __reduce_or_sync(0xffffffffu, m);
+          if (any) {
+            // Rare: some row of this warp beat a threshold in this 16-query chunk.  Reserve the
+            // slots of ALL affected queries first (one atomic per query, all in flight together),
+            // then write — one L2 round trip per chunk instead of one per query.
+            int slot0[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              slot0[j] = 0;
+              if ((any >> j) & 1u) {
+                const uint32_t b = __ballot_sync(0xffffffffu, (m >> j) & 1u);
+                if (lane == __ffs(b) - 1) slot0[j] = atomicAdd(a.cnt + (c0 + j), __popc(b));
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if ((any >> j) & 1u) {
+                const bool pass = (m >> j) & 1u;
+                const uint32_t b = __ballot_sync(0xffffffffu, pass);
+                const int s0 = __shfl_sync(0xffffffffu, slot0[j], __ffs(b) - 1);
+                if (pass) {
+                  const int q = c0 + j;
+                  const int slot = s0 + __popc(b & lt_mask);
+                  if (slot < a.C)
+                    a.cand[static_cast<int64_t>(q) * a.C + slot] = pack_cand(__uint_as_float(v[j]), static_cast<uint32_t>(row));
+                  else
+                    a.ovf[q] = 1;
+                }
+              }
             }
           }
         }

@@ -17,7 +17,8 @@ __device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
   return r;
 }
 
-// One warp per row: write the bf16 shadow row (round-to-nearest) and fold the row's norm^2 bound
+// One warp per row: write the bf16 shadow row (round-to-nearest, K-block-major tiled layout — 16
+// lanes fill one 128-byte K-block segment) and fold the row's norm^2 bound
 // into *maxnorm2_bits (float bits; valid because the values are non-negative).
 // HBM traffic per row: 3072 B read + 1536 B written.
 __global__ void __launch_bounds__(256) convert_rows_kernel(const float* __restrict__ x32,
@@ -30,13 +31,12 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const float* __restri
   float wmax = 0.f;
   for (int64_t r = warp; r < n_rows; r += nwarps) {
     const float4* src = reinterpret_cast<const float4*>(x32 + (row0 + r) * kD);
-    uint2* dst = x16 ? reinterpret_cast<uint2*>(x16 + (row0 + r) * kD) : nullptr;
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < kF4PerLane; ++i) {
       float4 v = ldg_stream_f4(src + lane + 32 * i);
       ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-      if (dst) dst[lane + 32 * i] = pack_bf16x4(v);
+      if (x16) *reinterpret_cast<uint2*>(x16 + shadow_index(row0 + r, 4 * (lane + 32 * i))) = pack_bf16x4(v);
     }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
@@ -83,7 +83,6 @@ __global__ void __launch_bounds__(256) synth_rows_kernel(float* __restrict__ x32
     // ss <= 768 * 510^2 < 2^31.  IEEE sqrt and division: bit-identical to the host restatement.
     const float inv = (ss > 0) ? __fdiv_rn(norm, __fsqrt_rn(static_cast<float>(ss))) : 0.f;
     float4* dst32 = reinterpret_cast<float4*>(x32 + (dst_row0 + r) * kD);
-    uint2* dst16 = x16 ? reinterpret_cast<uint2*>(x16 + (dst_row0 + r) * kD) : nullptr;
     float fs = 0.f;
 #pragma unroll
     for (int i = 0; i < kF4PerLane; ++i) {
@@ -94,7 +93,7 @@ __global__ void __launch_bounds__(256) synth_rows_kernel(float* __restrict__ x32
       v.w = __fmul_rn(static_cast<float>(comp[i][3]), inv);
       fs += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
       dst32[lane + 32 * i] = v;
-      if (dst16) dst16[lane + 32 * i] = pack_bf16x4(v);
+      if (x16) *reinterpret_cast<uint2*>(x16 + shadow_index(dst_row0 + r, 4 * (lane + 32 * i))) = pack_bf16x4(v);
     }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, s);

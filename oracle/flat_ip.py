@@ -234,12 +234,14 @@ def truth_fp64(x: np.ndarray, xb: np.ndarray, k: int, block: int = 262144):
     return D, I
 
 
-def compare(D, I, D_ref, I_ref, score_of=None, rtol: float = 1e-5):
+def compare(D, I, D_ref, I_ref, score_of=None, rtol: float = 1e-5, atol: float = 0.0):
     """Parity comparator (BASELINE.json north_star): ids must match the reference position by
     position except where the two ids involved have scores within `rtol` relative (a tie: swap
     inside a tie group, or exchange across the k-th boundary with a tied (k+1)-th); scores must agree
     within `rtol` relative.  `score_of(q, ids) -> float64 scores` supplies exact scores for ids that
-    appear in only one of the two lists (needed for boundary exchanges).
+    appear in only one of the two lists (needed for boundary exchanges).  `atol` is an absolute
+    floor for collections so small that near-zero scores are returned (a relative bound on a score
+    of 1e-4 is below the fp32 rounding of the reference itself); 0 for real top-k regimes.
 
     Returns dict(exact_rows, tie_excused, violations, max_rel_score_err).
     """
@@ -255,9 +257,11 @@ def compare(D, I, D_ref, I_ref, score_of=None, rtol: float = 1e-5):
         valid = I_ref[q] >= 0
         denom = np.maximum(np.abs(D_ref[q][valid]), 1e-30)
         if valid.any():
-            rel = np.abs(D[q][valid] - D_ref[q][valid]) / denom
-            max_rel = max(max_rel, float(rel.max()))
-            violations += int((rel > rtol).sum())
+            err = np.abs(D[q][valid] - D_ref[q][valid])
+            rel = err / denom
+            bad = err > rtol * np.abs(D_ref[q][valid]) + atol
+            max_rel = max(max_rel, float(rel[~bad].max()) if (~bad).any() else 0.0, float(rel[bad].max()) if bad.any() else 0.0)
+            violations += int(bad.sum())
         if not np.array_equal(valid, I[q] >= 0):
             violations += 1
             continue
@@ -271,7 +275,7 @@ def compare(D, I, D_ref, I_ref, score_of=None, rtol: float = 1e-5):
                 sa, sb = score_of(q, np.array([a, b], dtype=np.int64))
             else:  # best effort without exact scores: the reference's own score for `a` if it lists it
                 sa, sb = ref_score.get(a, D[q, pos]), D_ref[q, pos]
-            if abs(sa - sb) <= rtol * max(abs(sa), abs(sb), 1e-30):
+            if abs(sa - sb) <= rtol * max(abs(sa), abs(sb), 1e-30) + atol:
                 tie_excused += 1
             else:
                 violations += 1

@@ -248,12 +248,14 @@ def test_driver_search_one_by_one_on_gpu_matches_reference_golden(name):
     np.testing.assert_array_equal(I[pad], Ig[pad])           # -1 wrapped to the block's last offset, like the reference
     score_of = lambda qi, ids: Q[qi].astype(np.float64) @ P[ids].astype(np.float64).T
     Dc, Dgc = np.where(pad, -1.0, D), np.where(pad, -1.0, Dg)
-    r = flat_ip.compare(Dc, I, Dgc, Ig, score_of, rtol=RTOL)
+    # these collections are tiny (down to 23 rows), so scores near 0 are returned: the golden D
+    # (fp32 sgemm) itself carries ~1e-8 absolute rounding, which a purely relative bound cannot absorb
+    r = flat_ip.compare(Dc, I, Dgc, Ig, score_of, rtol=RTOL, atol=1e-7)
     assert r["violations"] == 0, r
     if name != "ties_across_blocks":
         assert r["exact_rows"] == nq, r                      # small cases: no near-ties, ids identical
     if name != "short_block_wraps_minus_one":
-        r2 = flat_ip.compare(Dr, Ir, Dgc[:, :topN], Ig[:, :topN], score_of, rtol=RTOL)
+        r2 = flat_ip.compare(Dr, Ir, Dgc[:, :topN], Ig[:, :topN], score_of, rtol=RTOL, atol=1e-7)
         assert r2["violations"] == 0, r2
 
 
