@@ -91,7 +91,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -105,23 +105,28 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.tmp.flush()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         with open(self.tmp.name) as f:
             for line in f:
                 p = [x.strip() for x in line.split(",")]
                 if len(p) < 9:
                     continue
                 try:
-                    sm.append(float(p[1])); mx.append(float(p[2]))
+                    clk, cmax, watts = float(p[1]), float(p[2]), float(p[3])
                 except ValueError:
                     continue
+                if watts < 250.0:      # idle sample (before / after the load): not "under load"
+                    continue
+                sm.append(clk); mx.append(cmax); pw.append(watts)
                 for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
                     if val.lower().startswith("active"):
                         reasons.add(name)
         os.unlink(self.tmp.name)
         if sm:
             out["sm_mhz"] = statistics.median(sm)
+            out["sm_mhz_min"] = min(sm)
             out["sm_max_mhz"] = max(mx)
+            out["power_w_median"] = statistics.median(pw)
             out["reasons"] = sorted(reasons)
             out["samples"] = len(sm)
         return out

@@ -100,6 +100,8 @@ struct Workspace {
   int* ovf = nullptr;
   float* margin = nullptr;
   int* err = nullptr;
+  uint64_t* gath = nullptr;   // refresh scratch: dense copy of a segmented list
+  int* cnt2 = nullptr;        // [qp][max_pairs] per-pair append counts of the tensor engine
   // queries of one search
   int64_t nq_cap = 0;
   float* q32 = nullptr;
@@ -303,7 +305,9 @@ int ensure_pass_ws(Shard& S, int qp, int C) {
   qp = std::max(qp, W.qp_cap);
   C = std::max(C, W.C);
   dev_free(W.cand[0]); dev_free(W.cand[1]); dev_free(W.cnt); dev_free(W.tau); dev_free(W.tauP);
-  dev_free(W.ovf); dev_free(W.margin);
+  dev_free(W.ovf); dev_free(W.margin); dev_free(W.gath); dev_free(W.cnt2);
+  B2F_TRY(dev_alloc(&W.gath, static_cast<size_t>(qp) * C));
+  B2F_TRY(dev_alloc(&W.cnt2, static_cast<size_t>(qp) * 128));
   B2F_TRY(dev_alloc(&W.cand[0], static_cast<size_t>(qp) * C));
   B2F_TRY(dev_alloc(&W.cand[1], static_cast<size_t>(qp) * C));
   B2F_TRY(dev_alloc(&W.cnt, static_cast<size_t>(qp)));
@@ -385,22 +389,30 @@ struct PassPlan {
   bool exact;   // total-order keys, zero margin, bounded phases
   int qp;       // max queries per pass
   int C;        // candidate capacity per query
-  int64_t n0;   // rows of the dense phase
+  int64_t n0;   // rows of the dense (bootstrap) phase
+  int S;        // tensor engine: survivor area [0, S) of a list
+  int cap_p;    // tensor engine: private slots per (query, CTA pair) and launch
 };
 
 PassPlan make_plan(const b2f_index* idx, const Shard& S, int path, int k) {
   PassPlan p;
   p.path = path;
   p.exact = (path == B2F_PATH_SCAN_EXACT);
+  p.S = 0;
+  p.cap_p = 0;
   if (path == B2F_PATH_UMMA_BF16) {
     p.qp = kUmmaMaxQ;
-    p.n0 = static_cast<int64_t>(S.max_pairs) * kTileRows;  // one wave of pair tiles
+    p.n0 = static_cast<int64_t>(S.max_pairs) * 256;  // bootstrap phase: 256 rows per CTA pair
+    p.S = static_cast<int>(round_up(std::max(1024, 4 * k), 256));
+    // expected appends per (query, pair) in a phase: 2 (margin) * (growth-1) * k / pairs; x2 safety
+    const int64_t expect = 4ll * (std::max(2, idx->growth) - 1) * k / S.max_pairs;
+    p.cap_p = static_cast<int>(round_up(std::max<int64_t>(256, expect), 32));
+    p.C = p.S + S.max_pairs * p.cap_p;
   } else {
     p.qp = kScanMaxQ;
     p.n0 = 16384;
+    p.C = static_cast<int>(round_up(std::max<int64_t>(p.n0, 32ll * k), 256));
   }
-  p.C = static_cast<int>(std::max<int64_t>(p.n0, 32ll * k));
-  p.C = static_cast<int>(round_up(p.C, 256));
   return p;
 }
 
@@ -417,21 +429,19 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   cudaStream_t s = S.stream;
   CU_TRY(cudaMemsetAsync(W.cnt, 0, sizeof(int) * nqp, s));
   CU_TRY(cudaMemsetAsync(W.ovf, 0, sizeof(int) * nqp, s));
+  const bool tensor = plan.path == B2F_PATH_UMMA_BF16;
+  if (tensor) CU_TRY(cudaMemsetAsync(W.cnt2, 0, sizeof(int) * nqp * S.max_pairs, s));
   const double u = plan.path == B2F_PATH_UMMA_BF16 ? kUBf16 : kUScan;
   const float two_u = plan.exact ? 0.f : static_cast<float>(2.0 * u * (idx->margin_ppm * 1e-6) * 1.0000001);
   margin_kernel<<<(nqp + 127) / 128, 128, 0, s>>>(qnormp, S.maxnorm2, two_u, nqp, W.margin);
   st.launches += 1;
 
   int cur = 0;
-  CUtensorMap tmap_p, tmap_q;
-  int n_cols = 0, stages = 0, smem = 0;
-  if (plan.path == B2F_PATH_UMMA_BF16) {
-    n_cols = static_cast<int>(round_up(nqp, 16));
-    stages = umma_stages(n_cols);
-    smem = umma_smem_bytes(n_cols, stages);
+  CUtensorMap tmap_p;
+  if (tensor) {
+    // shadow = [row tiles x 12 K-blocks x tile rows, 64 columns] bf16; box = 128 x 128 B = 16 KB
     B2F_TRY(make_tmap_bf16(&tmap_p, S.x16, static_cast<uint64_t>(shadow_rows_padded(N)) * kNumKBlocks, kBlockK,
-                           kTileRowsCta));
-    B2F_TRY(make_tmap_bf16(&tmap_q, q16p, static_cast<uint64_t>(n_cols), kD, static_cast<uint32_t>(n_cols / 2)));
+                           kKBlocksPerStage * kTileRowsCta));
   }
 
   // Phase boundaries in rows.  Dense phase first, then geometric growth (or, in exact mode,
@@ -450,16 +460,15 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       const int te = static_cast<int>((end + kTileRows - 1) / kTileRows);
       if (end < N) end = static_cast<int64_t>(te) * kTileRows;  // phases end on tile boundaries
       UmmaArgs a;
-      a.n_rows = N; a.tile_begin = tb; a.tile_end = te; a.n_cols = n_cols; a.nq = nqp; a.stages = stages;
-      a.dense = dense ? 1 : 0; a.dense_row0 = 0; a.cand = W.cand[cur]; a.cnt = W.cnt; a.C = C;
-      a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
+      a.n_rows = N; a.tile_begin = tb; a.tile_end = te; a.nq = nqp; a.q16 = q16p;
+      a.dense = dense ? 1 : 0; a.cand = W.cand[cur]; a.C = C; a.S = plan.S; a.cap_p = plan.cap_p;
+      a.max_pairs = S.max_pairs; a.cnt2 = W.cnt2; a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
       const int pairs = std::min(S.max_pairs, te - tb);
       {
         ProfScope ps(idx, S, 0);
-        umma_score_select_kernel<<<2 * pairs, kUmmaThreads, smem, s>>>(tmap_p, tmap_q, a);
+        umma_score_select_kernel<<<2 * pairs, kUmmaThreads, kUmmaSmemBytes, s>>>(tmap_p, a);
       }
       st.score_rows += static_cast<double>(std::min<int64_t>(N, static_cast<int64_t>(te) * kTileRows) - begin);
-      if (dense) n_override = (te - tb) * kTileRows;
     } else {
       ScanArgs a;
       a.x32 = S.x32; a.row_begin = begin; a.row_end = end; a.q32 = q32p; a.nq_pass = nqp;
@@ -479,8 +488,9 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     CU_TRY(cudaGetLastError());
     {
       ProfScope ps(idx, S, 1);
-      refresh_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.cnt, C, k, plan.exact ? 1 : 0,
-                                                W.margin, W.tau, W.tauP, n_override);
+      refresh_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.gath, W.cnt, C, k, plan.exact ? 1 : 0,
+                                                W.margin, W.tau, W.tauP, n_override, plan.S, plan.cap_p,
+                                                tensor ? S.max_pairs : 0, W.cnt2, W.ovf);
     }
     CU_TRY(cudaGetLastError());
     cur ^= 1;
@@ -536,7 +546,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
   if (plan.path == B2F_PATH_UMMA_BF16) {
     static bool attr_set[64] = {false};
     if (!attr_set[S.dev & 63]) {
-      CU_TRY(cudaFuncSetAttribute(umma_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+      CU_TRY(cudaFuncSetAttribute(umma_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmemBytes));
       attr_set[S.dev & 63] = true;
     }
   } else {
@@ -659,7 +669,7 @@ int b2f_create(int d, const int* devices, int n_dev, b2f_index** out) {
       return fail(B2F_ERR_CUDA, m);
     }
     S.sm_count = prop.multiProcessorCount;
-    S.max_pairs = std::max(1, S.sm_count / 2);
+    S.max_pairs = std::min(128, std::max(1, S.sm_count / 2));
   }
   // peer access between shard devices (direct NVLink copies for the result gather)
   for (size_t i = 0; i < devs.size(); ++i)
@@ -685,6 +695,7 @@ void b2f_destroy(b2f_index* idx) {
     dev_free(S.x32); dev_free(S.x16); dev_free(S.idmap); dev_free(S.maxnorm2); dev_free(S.segs_d);
     dev_free(W.cand[0]); dev_free(W.cand[1]); dev_free(W.cnt); dev_free(W.tau); dev_free(W.tauP);
     dev_free(W.ovf); dev_free(W.margin); dev_free(W.err); dev_free(W.q32); dev_free(W.q16);
+    dev_free(W.gath); dev_free(W.cnt2);
     dev_free(W.qnorm); dev_free(W.ovf_all); dev_free(W.D); dev_free(W.I); dev_free(W.Dp); dev_free(W.Ip);
     dev_free(W.fbq); dev_free(W.fbD); dev_free(W.fbI);
     if (W.ovf_host) cudaFreeHost(W.ovf_host);

@@ -12,12 +12,13 @@ constexpr int kF4PerLane = kRowF4 / 32;  // 6 float4 per lane per row
 
 // ---------------------------------------------------------------------------------------------
 // Layout of the bf16 shadow copy streamed by the tensor engine: "K-block-major tiles".
-// Rows are grouped in tiles of 128; inside a tile the 12 K-blocks (64 columns = 128 bytes each)
-// are stored one after the other, each as 128 rows x 128 bytes.  One TMA stage (128 rows of one
-// K-block) is therefore ONE contiguous 16 KB read instead of 128 granules of 128 B strided by the
-// 1536-byte row pitch.  Element (row, col) lives at shadow_index(row, col) (in bf16 elements).
+// Rows are grouped in tiles of 32; inside a tile the 12 K-blocks (64 columns = 128 bytes each)
+// are stored one after the other, each as 32 rows x 128 bytes.  One TMA stage (32 rows of four
+// consecutive K-blocks) is therefore ONE contiguous 16 KB read instead of 128-byte granules strided
+// by the 1536-byte row pitch, and a CTA's whole tile is one contiguous 48 KB region.
+// Element (row, col) lives at shadow_index(row, col) (in bf16 elements).
 // ---------------------------------------------------------------------------------------------
-constexpr int kShadowTileRows = 128;
+constexpr int kShadowTileRows = 32;
 constexpr int kShadowKBlock = 64;
 __host__ __device__ __forceinline__ int64_t shadow_index(int64_t row, int col) {
   const int64_t tile = row / kShadowTileRows;

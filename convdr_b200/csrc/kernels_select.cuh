@@ -82,9 +82,10 @@ __device__ int block_count_valid(const uint64_t* __restrict__ in, int n, SelectS
   return r;
 }
 
-// Copy every non-empty record >= T from in[0..n) to out[0..); returns how many.  Order arbitrary.
+// Copy every non-empty record >= T from in[0..n) to out[0..limit); returns how many qualified
+// (which may exceed `limit`: the caller flags the overflow).  Order arbitrary.
 __device__ int block_compact(const uint64_t* __restrict__ in, int n, uint64_t T,
-                             uint64_t* __restrict__ out, SelectSmem& sm) {
+                             uint64_t* __restrict__ out, int limit, SelectSmem& sm) {
   if (threadIdx.x == 0) sm.count = 0;
   __syncthreads();
   for (int i0 = 0; i0 < n; i0 += kSelThreads) {
@@ -97,13 +98,45 @@ __device__ int block_compact(const uint64_t* __restrict__ in, int n, uint64_t T,
       unsigned int base = 0;
       if (lane == 0) base = atomicAdd(&sm.count, __popc(b));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (keep) out[base + __popc(b & ((1u << lane) - 1u))] = key;
+      const unsigned int pos = base + __popc(b & ((1u << lane) - 1u));
+      if (keep && pos < static_cast<unsigned int>(limit)) out[pos] = key;
     }
   }
   __syncthreads();
   const int m = static_cast<int>(sm.count);
   __syncthreads();
   return m;
+}
+
+// Gather the valid entries of a segmented candidate list (survivors [0,m) + one private area per
+// CTA pair, see kernels_umma.cuh UmmaArgs) into a dense array; returns the entry count and clears
+// the per-pair counters for the next launch.
+__device__ int block_gather_segments(const uint64_t* __restrict__ in, int m, int S, int cap_p, int max_pairs,
+                                     int* __restrict__ cnt2q, uint64_t* __restrict__ gath, SelectSmem& sm,
+                                     int* seg_off /* smem [max_pairs] */) {
+  for (int i = threadIdx.x; i < m; i += kSelThreads) gath[i] = in[i];
+  int total = 0;
+  for (int p0 = 0; p0 < max_pairs; p0 += kSelThreads) {   // exclusive scan of the per-pair counts
+    const int p = p0 + threadIdx.x;
+    const unsigned int c = (p < max_pairs) ? static_cast<unsigned int>(cnt2q[p]) : 0u;
+    const unsigned int inc = block_inclusive_scan(c, sm);
+    if (p < max_pairs) seg_off[p] = total + static_cast<int>(inc - c);
+    if (threadIdx.x == kSelThreads - 1) sm.count = inc;
+    __syncthreads();
+    total += static_cast<int>(sm.count);
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int p = warp; p < max_pairs; p += kSelThreads / 32) {
+    const int c = (p + 1 < max_pairs ? seg_off[p + 1] : total) - seg_off[p];
+    const uint64_t* src = in + S + static_cast<int64_t>(p) * cap_p;
+    uint64_t* dst = gath + m + seg_off[p];
+    for (int e = lane; e < c; e += 32) dst[e] = src[e];
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < max_pairs; p += kSelThreads) cnt2q[p] = 0;
+  __syncthreads();
+  return m + total;
 }
 
 // Threshold refresh between phases, one block per query of the pass.
@@ -113,15 +146,26 @@ __device__ int block_compact(const uint64_t* __restrict__ in, int n, uint64_t T,
 //   exact mode: scores are final; tauP = the k-th largest record, survivors are exactly the top k.
 // With fewer than k valid records nothing can be rejected yet (tau = -inf / tauP = 0).
 __global__ void __launch_bounds__(kSelThreads) refresh_kernel(
-    const uint64_t* __restrict__ cand_in, uint64_t* __restrict__ cand_out, int* __restrict__ cnt,
-    int C, int k, int exact, const float* __restrict__ margin, float* __restrict__ tau,
-    uint64_t* __restrict__ tauP, int n_override) {
+    const uint64_t* __restrict__ cand_in, uint64_t* __restrict__ cand_out, uint64_t* __restrict__ gath,
+    int* __restrict__ cnt, int C, int k, int exact, const float* __restrict__ margin,
+    float* __restrict__ tau, uint64_t* __restrict__ tauP, int n_override, int S, int cap_p, int max_pairs,
+    int* __restrict__ cnt2, int* __restrict__ ovf) {
   __shared__ SelectSmem sm;
+  __shared__ int seg_off[128];
   const int q = blockIdx.x;
   const uint64_t* in = cand_in + static_cast<int64_t>(q) * C;
   uint64_t* out = cand_out + static_cast<int64_t>(q) * C;
-  int n = n_override >= 0 ? n_override : cnt[q];
-  if (n > C) n = C;
+  int n;
+  int limit = C;
+  if (max_pairs > 0) {   // segmented list written by the tensor engine
+    uint64_t* g = gath + static_cast<int64_t>(q) * C;
+    n = block_gather_segments(in, min(cnt[q], S), S, cap_p, max_pairs, cnt2 + q * max_pairs, g, sm, seg_off);
+    in = g;
+    limit = S;
+  } else {
+    n = n_override >= 0 ? n_override : cnt[q];
+    if (n > C) n = C;
+  }
   const int nvalid = block_count_valid(in, n, sm);
   uint64_t T = 0ull;
   float t = -INFINITY;
@@ -135,11 +179,12 @@ __global__ void __launch_bounds__(kSelThreads) refresh_kernel(
       T = static_cast<uint64_t>(fkey(t)) << 32;
     }
   }
-  const int m = block_compact(in, n, T, out, sm);
+  const int m = block_compact(in, n, T, out, limit, sm);
   if (threadIdx.x == 0) {
-    cnt[q] = m;
+    cnt[q] = min(m, limit);
     tau[q] = t;
     tauP[q] = T;
+    if (m > limit) ovf[q] = 1;   // more rows within the error margin of the k-th score than the list holds
   }
 }
 
@@ -193,7 +238,7 @@ __global__ void __launch_bounds__(kSelThreads) final_kernel(
     const int nvalid = block_count_valid(src, n, sm);
     uint64_t T = 0ull;
     if (nvalid >= k) T = block_kth_prefix(src, n, k, 8, sm);
-    n = block_compact(src, n, T, dst, sm);  // == min(nvalid, k) <= kSortCap
+    n = block_compact(src, n, T, dst, kSortCap, sm);  // == min(nvalid, k) <= kSortCap
     uint64_t* t = src; src = dst; dst = t;
   }
   int P = 32;

@@ -1,13 +1,19 @@
 // kernels_umma.cuh — the tensor-core scoring engine (sm_100a): a fused score + select kernel.
 //
-//   HBM (bf16 shadow rows) --TMA, 128B swizzle--> smem ring --tcgen05.mma cta_group::2--> TMEM
-//   TMEM --tcgen05.ld--> registers --threshold filter--> candidate lists (global atomics, rare)
+//   queries  : bf16, loaded ONCE per launch into TMEM (tcgen05.st) — the A operand of every MMA
+//   passages : bf16 shadow tiles  HBM --TMA (contiguous 16 KB, 128B swizzle)--> 14-stage smem ring
+//   scores   : tcgen05.mma cta_group::2 (A from TMEM, B from smem) --> TMEM accumulator
+//   select   : tcgen05.ld --> one QUERY per epilogue thread, threshold in a register,
+//              survivors appended to a (query, CTA pair)-private area of the candidate list:
+//              no atomics, no shared memory, no cross-thread traffic
 //
-// One CTA pair (2 SMs) owns a tile of 256 passage rows (128 per CTA, the MMA M dimension) and all
-// queries of the pass (MMA N <= 192, split in halves across the pair's shared memory, resident for
-// the whole launch).  K = 768 is walked in 12 blocks of 64 bf16 (one 128-byte swizzle span).
-// The [rows x queries] score tile never leaves the SM: accumulators live in TMEM (2 stages of 256
-// columns) and the epilogue keeps only scores >= the per-query threshold.
+// One CTA pair (2 SMs) holds up to 256 queries (128 TMEM lanes per CTA, the MMA M dimension) and
+// walks tiles of 64 passage rows (32 per CTA, the MMA N dimension; two accumulator stages of 64
+// TMEM columns, so the epilogue of tile i overlaps the MMAs of tile i+1).  Keeping the queries in TMEM
+// instead of shared memory leaves the whole 227 KB of smem to the passage ring: ~224 KB in flight
+// per SM is what lets a latency-bound HBM stream reach the roofline (with the queries in smem only
+// 80 KB fit and the kernel stalled at ~75 % — profiles/r01).  K = 768 is walked in 3 stages of four
+// 64-column K-blocks.  The [queries x rows] score tile never leaves the SM.
 //
 // Replaces the arithmetic of `index.search` (reference drivers/run_convdr_inference.py:182) —
 // FAISS's `nq >= 20` branch: blocked sgemm + per-row heap (upstream utils/distances.cpp), and
@@ -19,42 +25,42 @@
 namespace b2f {
 
 constexpr int kUmmaThreads = 256;
-constexpr int kBlockK = 64;                    // bf16 per K block = 128 bytes
+constexpr int kBlockK = 64;                    // bf16 per K-block = 128 bytes (one swizzle span)
 constexpr int kNumKBlocks = kD / kBlockK;      // 12
-constexpr int kTileRowsCta = 128;
-constexpr int kTileRows = 256;                 // per CTA pair
-constexpr int kStageBytes = kTileRowsCta * kBlockK * 2;  // 16 KB
-constexpr int kMaxStages = 8;
-constexpr int kUmmaMaxQ = 192;
-constexpr int kAccStride = 256;                // TMEM columns per accumulator stage
+constexpr int kTileRowsCta = kShadowTileRows;  // passage rows per CTA per tile (32)
+constexpr int kTileRows = 2 * kTileRowsCta;    // per CTA pair = MMA N (64)
+constexpr int kStageBytes = 16384;             // one TMA box, contiguous in HBM
+constexpr int kSubTileBytes = kTileRowsCta * 128;                   // one K-block of a CTA tile
+constexpr int kKBlocksPerStage = kStageBytes / kSubTileBytes;       // 4
+constexpr int kStagesPerTile = kNumKBlocks / kKBlocksPerStage;      // 3
+constexpr int kNumStages = 14;
+constexpr int kUmmaMaxQ = 256;                 // queries per pass = MMA M (both CTAs)
 constexpr int kTmemCols = 512;
-constexpr int kUmmaTailBytes = 2048;           // barriers + tmem pointer + thresholds
-constexpr int kSmemLimit = 232448;             // 227 KB opt-in maximum per CTA
+constexpr int kTmemColsA = kD / 2;             // 384 columns: 128 lanes x 768 bf16
+constexpr int kTmemColD = kTmemColsA;          // accumulators: columns [384, 512)
+constexpr int kAccStages = (kTmemCols - kTmemColsA) / kTileRows;    // 2 (double-buffered)
+constexpr int kUmmaTailBytes = 1024;           // barriers + tmem pointer
+constexpr int kUmmaSmemBytes = kNumStages * kStageBytes + kUmmaTailBytes + 1024;  // + alignment slack
+static_assert(kUmmaSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
+static_assert(kAccStages >= 1 && kAccStages <= 2, "TMEM budget: 384 query columns + accumulators in 128 columns");
+static_assert(kTileRows % 32 == 0 && kNumKBlocks % kKBlocksPerStage == 0, "tile shape");
 
 struct UmmaArgs {
   int64_t n_rows;             // valid rows of the shard
-  int tile_begin, tile_end;   // pair tiles of 256 rows
-  int n_cols;                 // MMA N: padded query count, multiple of 16, 16..192
-  int nq;                     // valid queries (<= n_cols)
-  int stages;                 // smem ring depth (2..8)
-  int dense;                  // 1: store every score at slot (row - dense_row0)
-  int64_t dense_row0;
-  uint64_t* cand;             // [nq][C]
-  int* cnt;                   // [nq]
-  int C;
+  int tile_begin, tile_end;   // pair tiles of 128 rows
+  int nq;                     // valid queries of the pass (<= 256)
+  const __nv_bfloat16* q16;   // pass queries, row-major [>= nq, 768] bf16
+  int dense;                  // 1: store every score (bootstrap phase), 0: threshold filter
+  // Candidate list of query q: cand[q*C .. q*C+C).  [0, S) holds the survivors of earlier phases
+  // (written by refresh_kernel); the rest is split in `max_pairs` private areas of `cap_p` slots,
+  // one per CTA pair, so the thread that owns (query, pair) appends without any atomic.
+  uint64_t* cand;
+  int C, S, cap_p, max_pairs;
+  int* cnt2;                  // [nq][max_pairs] entries written by each pair in this launch
   const float* tau;           // [nq]
-  int* ovf;                   // [nq]
+  int* ovf;                   // [nq] set when a private area was too small
   int* err;                   // device error flag (barrier timeout)
 };
-
-inline int umma_q_bytes(int n_cols) { return kNumKBlocks * (n_cols / 2) * 128; }
-inline int umma_stages(int n_cols) {
-  int s = (kSmemLimit - kUmmaTailBytes - 1024 /*alignment slack*/ - umma_q_bytes(n_cols)) / kStageBytes;
-  return s > kMaxStages ? kMaxStages : s;
-}
-inline int umma_smem_bytes(int n_cols, int stages) {
-  return umma_q_bytes(n_cols) + stages * kStageBytes + kUmmaTailBytes + 1024;
-}
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -179,35 +185,85 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
 constexpr uint64_t kHintEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kHintEvictLast = 0x14F0000000000000ull;
 
+// D[tmem] (+)= A[tmem] * B[smem]^T : the queries (A) stay resident in tensor memory.
+__device__ __forceinline__ void umma_bf16_2sm_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// v[i] for a warp-uniform runtime i in [0,32): a dense switch (jump table) keeps v in registers —
+// indexing the array dynamically would demote all 128 scores to local memory.
+__device__ __forceinline__ uint32_t pick32(const uint32_t* v, int i) {
+  switch (i) {
+#define B2F_PICK(n) case n: return v[n];
+    B2F_PICK(0) B2F_PICK(1) B2F_PICK(2) B2F_PICK(3) B2F_PICK(4) B2F_PICK(5) B2F_PICK(6) B2F_PICK(7)
+    B2F_PICK(8) B2F_PICK(9) B2F_PICK(10) B2F_PICK(11) B2F_PICK(12) B2F_PICK(13) B2F_PICK(14) B2F_PICK(15)
+    B2F_PICK(16) B2F_PICK(17) B2F_PICK(18) B2F_PICK(19) B2F_PICK(20) B2F_PICK(21) B2F_PICK(22) B2F_PICK(23)
+    B2F_PICK(24) B2F_PICK(25) B2F_PICK(26) B2F_PICK(27) B2F_PICK(28) B2F_PICK(29) B2F_PICK(30)
+#undef B2F_PICK
+    default: return v[31];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // The kernel.  Grid = 2 * (number of CTA pairs), cluster (2,1,1), 256 threads:
-//   warp 0 lane 0 : TMA producer (both CTAs: own 128 rows; own half of the queries once)
+//   warp 0 lane 0 : TMA producer (both CTAs stream their own 64 rows of every tile)
 //   warp 1 lane 0 : MMA issuer (leader CTA only)
 //   warp 2        : TMEM allocation / release
-//   warps 4..7    : epilogue — TMEM lane quarter (warp % 4), one passage row per thread
+//   warps 4..7    : load the queries into TMEM, then epilogue — thread (rank, lane) owns query
+//                   128*rank + 32*(warp%4) + lane
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
-    umma_score_select_kernel(const __grid_constant__ CUtensorMap tmap_p,
-                             const __grid_constant__ CUtensorMap tmap_q, const UmmaArgs a) {
+    umma_score_select_kernel(const __grid_constant__ CUtensorMap tmap_p, const UmmaArgs a) {
   extern __shared__ unsigned char umma_smem_raw[];
   const uint32_t raw = smem_u32(umma_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 1024-byte alignment for the 128B swizzle atoms
   unsigned char* base_ptr = umma_smem_raw + (base - raw);
-
-  const int n_half = a.n_cols >> 1;
-  const uint32_t q_kblock_bytes = static_cast<uint32_t>(n_half) * 128u;
-  const uint32_t q_bytes = kNumKBlocks * q_kblock_bytes;
-  const uint32_t smem_q = base;
-  const uint32_t smem_a = base + q_bytes;
-  const uint32_t tail = smem_a + static_cast<uint32_t>(a.stages) * kStageBytes;
-  const uint32_t bar_full = tail;                      // [kMaxStages]
-  const uint32_t bar_empty = tail + 8 * kMaxStages;    // [kMaxStages]
-  const uint32_t bar_qfull = tail + 16 * kMaxStages;
-  const uint32_t bar_tfull = bar_qfull + 8;            // [2]
-  const uint32_t bar_tempty = bar_tfull + 16;          // [2]
-  unsigned char* tail_ptr = base_ptr + q_bytes + static_cast<uint32_t>(a.stages) * kStageBytes;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail_ptr + 16 * kMaxStages + 8 + 16 + 16);
-  float* tau_s = reinterpret_cast<float*>(tail_ptr + 256);  // [kUmmaMaxQ]
+  const uint32_t smem_b = base;                                   // [kNumStages][16 KB]
+  const uint32_t tail = smem_b + kNumStages * kStageBytes;
+  const uint32_t bar_full = tail;                                 // [kNumStages]
+  const uint32_t bar_empty = tail + 8 * kNumStages;               // [kNumStages]
+  const uint32_t bar_qready = tail + 16 * kNumStages;
+  const uint32_t bar_tfull = bar_qready + 8;                      // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;                     // [2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(base_ptr + kNumStages * kStageBytes + 16 * kNumStages + 40);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -215,16 +271,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
 
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmap_p);
-    prefetch_tmap(&tmap_q);
-  }
+  if (warp == 0 && lane == 0) prefetch_tmap(&tmap_p);
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kMaxStages; ++s) {
+    for (int s = 0; s < kNumStages; ++s) {
       mbar_init(bar_full + 8 * s, 2);   // leader's expect_tx arrive + peer's remote arrive
       mbar_init(bar_empty + 8 * s, 1);  // one multicast commit
     }
-    mbar_init(bar_qfull, 2);
+    mbar_init(bar_qready, 8);           // 4 query-loading warps x 2 CTAs
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);   // one multicast commit
       mbar_init(bar_tempty + 8 * s, 8);  // 4 epilogue warps x 2 CTAs (leader's copy is the one used)
@@ -236,8 +289,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
                  ::"r"(smem_u32(tmem_ptr_s)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < kUmmaMaxQ; i += kUmmaThreads)
-    tau_s[i] = (i < a.nq && !a.dense) ? a.tau[i] : INFINITY;
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -246,119 +297,138 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    const uint32_t qfull_leader = mapa_u32(bar_qfull, 0);
-    if (leader) mbar_arrive_expect_tx(bar_qfull, 2u * q_bytes);
-    else mbar_arrive_cluster(qfull_leader);
-    for (int kb = 0; kb < kNumKBlocks; ++kb)
-      tma_load_2d_2sm(smem_q + kb * q_kblock_bytes, &tmap_q, qfull_leader, kb * kBlockK,
-                      static_cast<int>(cta_rank) * n_half, kHintEvictLast);
     uint32_t stage = 0, phase = 0;
     for (int tile = a.tile_begin + pair; tile < a.tile_end; tile += npairs) {
-      // shadow layout: CTA tile t = 2*tile + rank, K-block kb -> 128 consecutive 128-byte rows
-      const int blk0 = (tile * 2 + static_cast<int>(cta_rank)) * kNumKBlocks;
-      for (int kb = 0; kb < kNumKBlocks; ++kb) {
+      // shadow layout (common.cuh): CTA tile = 2*tile + rank; kKBlocksPerStage consecutive K-blocks
+      // of it are 128 consecutive 128-byte rows = one contiguous 16 KB box
+      const int row0 = (tile * 2 + static_cast<int>(cta_rank)) * kNumKBlocks * kTileRowsCta;
+      for (int st = 0; st < kStagesPerTile; ++st) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1u, a.err);
         const uint32_t full_leader = mapa_u32(bar_full + 8 * stage, 0);
         if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2u * kStageBytes);
         else mbar_arrive_cluster(full_leader);
-        tma_load_2d_2sm(smem_a + stage * kStageBytes, &tmap_p, full_leader, 0, (blk0 + kb) * kTileRowsCta,
-                        kHintEvictFirst);
-        if (++stage == static_cast<uint32_t>(a.stages)) { stage = 0; phase ^= 1u; }
+        tma_load_2d_2sm(smem_b + stage * kStageBytes, &tmap_p, full_leader, 0,
+                        row0 + st * (kKBlocksPerStage * kTileRowsCta), kHintEvictFirst);
+        if (++stage == kNumStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
-    // ===================== MMA issuer (leader CTA) =====================
-    const uint32_t idesc = umma_idesc_bf16(256, a.n_cols);
-    mbar_wait(bar_qfull, 0, a.err);
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (leader CTA; the whole warp waits, one elected lane issues) =====
+    const uint32_t idesc = umma_idesc_bf16(256, kTileRows);
+    const bool elected = elect_one();
+    mbar_wait(bar_qready, 0, a.err);   // both CTAs have their queries in TMEM
     tc_fence_after();
     uint32_t stage = 0, phase = 0;
     int it = 0;
     for (int tile = a.tile_begin + pair; tile < a.tile_end; tile += npairs, ++it) {
-      const uint32_t as = it & 1, aph = (it >> 1) & 1;
-      mbar_wait(bar_tempty + 8 * as, aph ^ 1u, a.err);
+      const uint32_t as = static_cast<uint32_t>(it) % kAccStages, aph = (static_cast<uint32_t>(it) / kAccStages) & 1u;
+      mbar_wait(bar_tempty + 8 * as, aph ^ 1u, a.err);   // epilogue has drained this accumulator stage
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + as * kAccStride;
-      for (int kb = 0; kb < kNumKBlocks; ++kb) {
+      const uint32_t tmem_d = tmem_base + kTmemColD + as * kTileRows;
+      for (int st = 0; st < kStagesPerTile; ++st) {
         mbar_wait(bar_full + 8 * stage, phase, a.err);
         tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_a + stage * kStageBytes);
-        const uint64_t bdesc = umma_desc_sw128(smem_q + kb * q_kblock_bytes);
+        if (elected) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)  // UMMA K = 16 bf16 = 32 bytes = 2 descriptor units
-          umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        umma_commit_pair(bar_empty + 8 * stage);  // frees this smem stage in both CTAs
-        if (kb == kNumKBlocks - 1) umma_commit_pair(bar_tfull + 8 * as);  // accumulator ready
-        if (++stage == static_cast<uint32_t>(a.stages)) { stage = 0; phase ^= 1u; }
+          for (int j = 0; j < kKBlocksPerStage; ++j) {
+            const uint64_t bdesc = umma_desc_sw128(smem_b + stage * kStageBytes + j * kSubTileBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {   // UMMA K = 16 bf16: 8 TMEM columns of A, 32 bytes of B
+              const int kstep = (st * kKBlocksPerStage + j) * (kBlockK / 16) + k;
+              umma_bf16_2sm_ts(tmem_d, tmem_base + 8 * kstep, bdesc + 2 * k, idesc, kstep != 0);
+            }
+          }
+          umma_commit_pair(bar_empty + 8 * stage);                            // frees this smem stage in both CTAs
+          if (st == kStagesPerTile - 1) umma_commit_pair(bar_tfull + 8 * as); // accumulator ready
+        }
+        __syncwarp();
+        if (++stage == kNumStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: filter + append =====================
+    // ===================== queries -> TMEM, then epilogue =====================
     const int ew = warp & 3;
-    const uint32_t tempty_leader0 = mapa_u32(bar_tempty, 0);
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    const int q = static_cast<int>(cta_rank) * 128 + ew * 32 + lane;
+    const bool q_ok = q < a.nq;
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(a.q16 + static_cast<int64_t>(q_ok ? q : 0) * kD);
+#pragma unroll 1
+      for (int c = 0; c < kTmemColsA / 32; ++c) {   // 32 columns = 64 bf16 = 128 bytes per step
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4 t = q_ok ? __ldg(src + c * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
+          w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+        }
+        tmem_st_x32(lane_addr + 32 * c, w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(bar_qready, 0));
+    }
+    const float tau = (q_ok && !a.dense) ? a.tau[q] : INFINITY;
+    uint64_t* my_list = a.cand + static_cast<int64_t>(q_ok ? q : 0) * a.C + a.S + static_cast<int64_t>(pair) * a.cap_p;
+    int n_mine = 0;   // entries this thread appended for (query q, this pair)
+    const uint32_t tempty_leader = mapa_u32(bar_tempty, 0);
     int it = 0;
     for (int tile = a.tile_begin + pair; tile < a.tile_end; tile += npairs, ++it) {
-      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const uint32_t as = static_cast<uint32_t>(it) % kAccStages, aph = (static_cast<uint32_t>(it) / kAccStages) & 1u;
       mbar_wait(bar_tfull + 8 * as, aph, a.err);
       tc_fence_after();
-      const int64_t row = static_cast<int64_t>(tile) * kTileRows + cta_rank * kTileRowsCta + ew * 32 + lane;
-      const bool row_ok = row < a.n_rows;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * kAccStride;
-      for (int c0 = 0; c0 < a.n_cols; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(taddr + c0, v);
-        tmem_ld_wait();
-        if (a.dense) {
-          const int64_t slot = row - a.dense_row0;
+      uint32_t v[kTileRows];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int q = c0 + j;
-            if (q < a.nq)
-              a.cand[static_cast<int64_t>(q) * a.C + slot] =
-                  row_ok ? pack_cand(__uint_as_float(v[j]), static_cast<uint32_t>(row)) : 0ull;
+      for (int w = 0; w < kTileRows / 32; ++w) tmem_ld_x32(lane_addr + kTmemColD + as * kTileRows + 32 * w, v + 32 * w);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * as);   // this accumulator stage is free again
+      const int64_t row0 = static_cast<int64_t>(tile) * kTileRows;
+      const int n_valid = static_cast<int>(min(static_cast<int64_t>(kTileRows), a.n_rows - row0));
+      if (a.dense) {
+        // bootstrap: every score of this tile goes to the private area (zeros for rows past the end)
+        if (q_ok && n_mine + kTileRows <= a.cap_p) {
+          uint64_t* dst = my_list + n_mine;
+#pragma unroll
+          for (int c = 0; c < kTileRows; c += 2) {
+            ulonglong2 o;
+            o.x = (c < n_valid) ? pack_cand(__uint_as_float(v[c]), static_cast<uint32_t>(row0 + c)) : 0ull;
+            o.y = (c + 1 < n_valid) ? pack_cand(__uint_as_float(v[c + 1]), static_cast<uint32_t>(row0 + c + 1)) : 0ull;
+            *reinterpret_cast<ulonglong2*>(dst + c) = o;
           }
-        } else {
+        }
+        n_mine += kTileRows;
+      } else {
+        if (n_valid < kTileRows) {   // only the last tile of the shard
+#pragma unroll
+          for (int c = 0; c < kTileRows; ++c)
+            if (c >= n_valid) v[c] = 0xff800000u;   // -inf
+        }
+        // Branch-free filter: one predicate bit per score (a taken branch per score costs ~25 cycles
+        // with a single warp per scheduler — profiles/r01).  Hits are rare; they are handled per
+        // 32-column word in a warp-uniform loop over the columns any lane flagged.
+#pragma unroll
+        for (int w = 0; w < kTileRows / 32; ++w) {
           uint32_t m = 0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            m |= (__uint_as_float(v[j]) >= tau_s[c0 + j]) ? (1u << j) : 0u;
-          if (!row_ok) m = 0;
-          const uint32_t any = __reduce_or_sync(0xffffffffu, m);
-          if (any) {
-            // Rare: some row of this warp beat a threshold in this 16-query chunk.  Reserve the
-            // slots of ALL affected queries first (one atomic per query, all in flight together),
-            // then write — one L2 round trip per chunk instead of one per query.
-            int slot0[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              slot0[j] = 0;
-              if ((any >> j) & 1u) {
-                const uint32_t b = __ballot_sync(0xffffffffu, (m >> j) & 1u);
-                if (lane == __ffs(b) - 1) slot0[j] = atomicAdd(a.cnt + (c0 + j), __popc(b));
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if ((any >> j) & 1u) {
-                const bool pass = (m >> j) & 1u;
-                const uint32_t b = __ballot_sync(0xffffffffu, pass);
-                const int s0 = __shfl_sync(0xffffffffu, slot0[j], __ffs(b) - 1);
-                if (pass) {
-                  const int q = c0 + j;
-                  const int slot = s0 + __popc(b & lt_mask);
-                  if (slot < a.C)
-                    a.cand[static_cast<int64_t>(q) * a.C + slot] = pack_cand(__uint_as_float(v[j]), static_cast<uint32_t>(row));
-                  else
-                    a.ovf[q] = 1;
-                }
-              }
+          for (int c = 0; c < 32; ++c) m |= (__uint_as_float(v[32 * w + c]) >= tau) ? (1u << c) : 0u;
+          uint32_t any = __reduce_or_sync(0xffffffffu, m);
+          while (any) {   // rare
+            const int c = __ffs(any) - 1;
+            any &= any - 1;
+            const uint32_t bits = pick32(v + 32 * w, c);
+            if ((m >> c) & 1u) {   // no atomics: the area is private to this thread
+              if (n_mine < a.cap_p) my_list[n_mine] = pack_cand(__uint_as_float(bits), static_cast<uint32_t>(row0 + 32 * w + c));
+              ++n_mine;
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * as);
+    }
+    if (q_ok) {
+      a.cnt2[q * a.max_pairs + pair] = min(n_mine, a.cap_p);
+      if (n_mine > a.cap_p) a.ovf[q] = 1;
     }
   }
   __syncwarp();
