@@ -176,7 +176,7 @@ struct b2f_index {
   // options
   int path = B2F_PATH_AUTO;
   int shadow = 1;
-  int growth = 16;
+  int growth = 32;
   int64_t margin_ppm = 1000000;
   int keep_on_reset = 1;
   int scan_max_auto = 4;  // AUTO: batches up to this size use the SIMT scan
@@ -402,11 +402,14 @@ PassPlan make_plan(const b2f_index* idx, const Shard& S, int path, int k) {
   p.cap_p = 0;
   if (path == B2F_PATH_UMMA_BF16) {
     p.qp = kUmmaMaxQ;
-    p.n0 = static_cast<int64_t>(S.max_pairs) * 256;  // bootstrap phase: 256 rows per CTA pair
+    // bootstrap (dense) phase: whole tiles per CTA pair, at least 8k rows (and 4096) in total
+    const int64_t wave = static_cast<int64_t>(S.max_pairs) * kTileRows;
+    const int64_t t0 = (std::max<int64_t>(4096, 8ll * k) + wave - 1) / wave;
+    p.n0 = t0 * wave;
     p.S = static_cast<int>(round_up(std::max(1024, 4 * k), 256));
     // expected appends per (query, pair) in a phase: 2 (margin) * (growth-1) * k / pairs; x2 safety
     const int64_t expect = 4ll * (std::max(2, idx->growth) - 1) * k / S.max_pairs;
-    p.cap_p = static_cast<int>(round_up(std::max<int64_t>(256, expect), 32));
+    p.cap_p = static_cast<int>(round_up(std::max<int64_t>(std::max<int64_t>(256, t0 * kTileRows), expect), 32));
     p.C = p.S + S.max_pairs * p.cap_p;
   } else {
     p.qp = kScanMaxQ;
@@ -501,9 +504,14 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   }
   {
     ProfScope ps(idx, S, 1);
-    final_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.cnt, C, k, plan.exact ? 0 : 1, q32p,
-                                            S.x32, S.segs_d, static_cast<int>(S.segs.size()),
-                                            S.has_ids ? S.idmap : nullptr, D_out, I_out, out_stride);
+    if (!plan.exact) {   // approximate engines: replace the prefilter scores by exact ones first
+      rescore_kernel<<<dim3(nqp, kRescoreSplit), kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.cnt, C, q32p, S.x32);
+      cur ^= 1;
+      st.launches += 1;
+    }
+    final_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.cnt, C, k, S.segs_d,
+                                            static_cast<int>(S.segs.size()), S.has_ids ? S.idmap : nullptr,
+                                            D_out, I_out, out_stride);
   }
   CU_TRY(cudaGetLastError());
   st.launches += 1;

@@ -199,46 +199,55 @@ __device__ __forceinline__ int64_t row_to_id(uint32_t row, const Seg* __restrict
   return segs[lo].global_start + (static_cast<int64_t>(row) - segs[lo].local_start);
 }
 
-// Final step of a pass, one block per query: exact rescoring of the surviving candidates
-// (fp64-accumulated dot, one warp per candidate), top-k by total order, sorted output.
-//   D_out / I_out: row stride `out_stride`, k entries written per query.
-__global__ void __launch_bounds__(kSelThreads) final_kernel(
-    uint64_t* __restrict__ cand_cur, uint64_t* __restrict__ cand_other, const int* __restrict__ cnt,
-    int C, int k, int rescore, const float* __restrict__ q32 /* pass queries [nq_pass, 768] */,
-    const float* __restrict__ x32, const Seg* __restrict__ segs, int nseg,
-    const int64_t* __restrict__ idmap, float* __restrict__ D_out, int64_t* __restrict__ I_out,
-    int64_t out_stride) {
-  __shared__ SelectSmem sm;
+// Exact rescoring of the surviving candidates of a pass: fp64-accumulated dot, one warp per
+// candidate, grid (queries, kRescoreSplit) so the ~2k random 3 KB row gathers per query are spread
+// over the whole GPU.  Writes pack(exact score, row) to cand_out at the same position.
+constexpr int kRescoreSplit = 8;
+__global__ void __launch_bounds__(kSelThreads) rescore_kernel(
+    const uint64_t* __restrict__ cand_in, uint64_t* __restrict__ cand_out, const int* __restrict__ cnt, int C,
+    const float* __restrict__ q32 /* pass queries [nq_pass, 768] */, const float* __restrict__ x32) {
   __shared__ __align__(16) float Qs[kD];
-  __shared__ uint64_t sortbuf[kSortCap];
   const int q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int n = cnt[q];
   if (n > C) n = C;
+  if (static_cast<int>(blockIdx.y) * (kSelThreads / 32) >= n) return;
+  for (int i = threadIdx.x; i < kD; i += kSelThreads) Qs[i] = q32[static_cast<int64_t>(q) * kD + i];
+  __syncthreads();
+  const float4* q4 = reinterpret_cast<const float4*>(Qs);
+  const uint64_t* src = cand_in + static_cast<int64_t>(q) * C;
+  uint64_t* dst = cand_out + static_cast<int64_t>(q) * C;
+  for (int c = blockIdx.y * (kSelThreads / 32) + warp; c < n; c += kRescoreSplit * (kSelThreads / 32)) {
+    const uint64_t rec = src[c];
+    uint64_t o = 0ull;
+    if (rec != 0ull) {  // warp-uniform
+      const uint32_t row = cand_row(rec);
+      const float s = exact_dot_warp(q4, reinterpret_cast<const float4*>(x32 + static_cast<int64_t>(row) * kD), lane);
+      o = pack_cand(s, row);
+    }
+    if (lane == 0) dst[c] = o;
+  }
+}
+
+// Final step of a pass, one block per query: top-k of the (exactly scored) candidates by the total
+// order (score desc, row asc), sorted output, row -> id translation.
+//   D_out / I_out: row stride `out_stride`, k entries written per query.
+__global__ void __launch_bounds__(kSelThreads) final_kernel(
+    uint64_t* __restrict__ cand_cur, uint64_t* __restrict__ cand_other, const int* __restrict__ cnt,
+    int C, int k, const Seg* __restrict__ segs, int nseg, const int64_t* __restrict__ idmap,
+    float* __restrict__ D_out, int64_t* __restrict__ I_out, int64_t out_stride) {
+  __shared__ SelectSmem sm;
+  __shared__ uint64_t sortbuf[kSortCap];
+  const int q = blockIdx.x;
+  int n = cnt[q];
+  if (n > C) n = C;
   uint64_t* src = cand_cur + static_cast<int64_t>(q) * C;
   uint64_t* dst = cand_other + static_cast<int64_t>(q) * C;
-  if (rescore) {
-    for (int i = threadIdx.x; i < kD; i += kSelThreads) Qs[i] = q32[static_cast<int64_t>(q) * kD + i];
-    __syncthreads();
-    const float4* q4 = reinterpret_cast<const float4*>(Qs);
-    for (int c = warp; c < n; c += kSelThreads / 32) {
-      const uint64_t rec = src[c];
-      uint64_t o = 0ull;
-      if (rec != 0ull) {  // warp-uniform
-        const uint32_t row = cand_row(rec);
-        const float s = exact_dot_warp(q4, reinterpret_cast<const float4*>(x32 + static_cast<int64_t>(row) * kD), lane);
-        o = pack_cand(s, row);
-      }
-      if (lane == 0) dst[c] = o;
-    }
-    __syncthreads();
-    uint64_t* t = src; src = dst; dst = t;
-  }
   if (n > kSortCap) {
     const int nvalid = block_count_valid(src, n, sm);
     uint64_t T = 0ull;
     if (nvalid >= k) T = block_kth_prefix(src, n, k, 8, sm);
-    n = block_compact(src, n, T, dst, kSortCap, sm);  // == min(nvalid, k) <= kSortCap
+    n = min(block_compact(src, n, T, dst, kSortCap, sm), kSortCap);  // == min(nvalid, k)
     uint64_t* t = src; src = dst; dst = t;
   }
   int P = 32;

@@ -228,20 +228,6 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// v[i] for a warp-uniform runtime i in [0,32): a dense switch (jump table) keeps v in registers —
-// indexing the array dynamically would demote all 128 scores to local memory.
-__device__ __forceinline__ uint32_t pick32(const uint32_t* v, int i) {
-  switch (i) {
-#define B2F_PICK(n) case n: return v[n];
-    B2F_PICK(0) B2F_PICK(1) B2F_PICK(2) B2F_PICK(3) B2F_PICK(4) B2F_PICK(5) B2F_PICK(6) B2F_PICK(7)
-    B2F_PICK(8) B2F_PICK(9) B2F_PICK(10) B2F_PICK(11) B2F_PICK(12) B2F_PICK(13) B2F_PICK(14) B2F_PICK(15)
-    B2F_PICK(16) B2F_PICK(17) B2F_PICK(18) B2F_PICK(19) B2F_PICK(20) B2F_PICK(21) B2F_PICK(22) B2F_PICK(23)
-    B2F_PICK(24) B2F_PICK(25) B2F_PICK(26) B2F_PICK(27) B2F_PICK(28) B2F_PICK(29) B2F_PICK(30)
-#undef B2F_PICK
-    default: return v[31];
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // The kernel.  Grid = 2 * (number of CTA pairs), cluster (2,1,1), 256 threads:
 //   warp 0 lane 0 : TMA producer (both CTAs stream their own 64 rows of every tile)
@@ -381,9 +367,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
 #pragma unroll
       for (int w = 0; w < kTileRows / 32; ++w) tmem_ld_x32(lane_addr + kTmemColD + as * kTileRows + 32 * w, v + 32 * w);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * as);   // this accumulator stage is free again
       const int64_t row0 = static_cast<int64_t>(tile) * kTileRows;
       const int n_valid = static_cast<int>(min(static_cast<int64_t>(kTileRows), a.n_rows - row0));
       if (a.dense) {
@@ -400,24 +383,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
         }
         n_mine += kTileRows;
       } else {
-        if (n_valid < kTileRows) {   // only the last tile of the shard
-#pragma unroll
-          for (int c = 0; c < kTileRows; ++c)
-            if (c >= n_valid) v[c] = 0xff800000u;   // -inf
-        }
         // Branch-free filter: one predicate bit per score (a taken branch per score costs ~25 cycles
         // with a single warp per scheduler — profiles/r01).  Hits are rare; they are handled per
-        // 32-column word in a warp-uniform loop over the columns any lane flagged.
+        // 32-column word in a warp-uniform loop over the columns any lane flagged, re-reading that
+        // single column from TMEM (a dynamic register index would demote v[] to local memory).
 #pragma unroll
         for (int w = 0; w < kTileRows / 32; ++w) {
           uint32_t m = 0;
 #pragma unroll
           for (int c = 0; c < 32; ++c) m |= (__uint_as_float(v[32 * w + c]) >= tau) ? (1u << c) : 0u;
+          if (32 * w + 32 > n_valid) m &= (n_valid > 32 * w) ? ((1u << (n_valid - 32 * w)) - 1u) : 0u;  // shard tail
           uint32_t any = __reduce_or_sync(0xffffffffu, m);
           while (any) {   // rare
             const int c = __ffs(any) - 1;
             any &= any - 1;
-            const uint32_t bits = pick32(v + 32 * w, c);
+            const uint32_t bits = tmem_ld_x1(lane_addr + kTmemColD + as * kTileRows + 32 * w + c);
+            tmem_ld_wait();
             if ((m >> c) & 1u) {   // no atomics: the area is private to this thread
               if (n_mine < a.cap_p) my_list[n_mine] = pack_cand(__uint_as_float(bits), static_cast<uint32_t>(row0 + 32 * w + c));
               ++n_mine;
@@ -425,6 +406,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * as);   // this accumulator stage is free again
     }
     if (q_ok) {
       a.cnt2[q * a.max_pairs + pair] = min(n_mine, a.cap_p);
