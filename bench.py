@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--k", type=int, default=TOPK)
     ap.add_argument("--path", default="auto")
     ap.add_argument("--growth", type=int, default=0, help="phase growth factor override (0 = engine default)")
+    ap.add_argument("--variant", type=int, default=0, help="tensor engine variant: 0 auto, 1 SS, 2 TS")
+    ap.add_argument("--l2-prefetch", type=int, default=1)
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
@@ -69,12 +71,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary."""
+def ncu_traffic_per_launch(rows_per_launch: float):
+    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/ncu_summary.json: bytes per row of the captured launch) scaled
+    to the rows one average launch of this run streams."""
     path = os.path.join(ROOT, "profiles", "ncu_summary.json")
     try:
         with open(path) as f:
-            return json.load(f).get("umma_score_select_kernel", {}).get("dram_bytes_per_launch")
+            per_row = json.load(f)["umma_score_select_kernel"]["dram_bytes_per_row"]
+        return per_row * rows_per_launch
     except Exception:
         return None
 
@@ -208,6 +213,8 @@ def run_b2f_arm(args):
     index.set_option("profile", 1)
     if args.growth:
         index.set_option("growth", args.growth)
+    index.set_option("umma_variant", args.variant)
+    index.set_option("l2_prefetch", args.l2_prefetch)
     sharded = ShardedFlatIP(index=index)
     t0 = time.perf_counter()
     lo, hi = sharded.add_synthetic(args.rows, seed=0, stream=0)
@@ -300,12 +307,14 @@ def run_b2f_arm(args):
                 "workload": f"CAsT-sized {args.rows}x768 collection (BASELINE.json configs[3]), {nq} queries, top-{k}, "
                             f"row-sharded over {n_gpus} GPU(s), {n_local} rows on rank 0",
                 "l2_policy": "inputs larger than L2 (>= 7 GB streamed per GPU per step vs 126 MB L2); no flush needed",
-                "engine_path": engine_path, "build_seconds": round(build_s, 2),
+                "engine_path": engine_path, "tensor_variant": args.variant, "l2_prefetch": args.l2_prefetch,
+                "build_seconds": round(build_s, 2),
                 "parallelism": f"shard{n_gpus}",
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": ncu_traffic_per_launch(),
+                "frac": achieved / peak if peak else None, "traffic": ncu_traffic_per_launch(rows_per_launch),
+                "algorithmic_bytes_per_launch": rows_per_launch * BYTES_STREAMED_PER_ROW,
                 "peak_source": peak_src, "kernel": "umma_score_select_kernel",
                 "bytes_per_row_streamed": BYTES_STREAMED_PER_ROW,
                 "achieved_fp32_equivalent": achieved * BYTES_ALGO_FP32_PER_ROW / BYTES_STREAMED_PER_ROW,

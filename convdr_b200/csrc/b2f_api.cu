@@ -26,6 +26,7 @@
 #include "kernels_scan.cuh"
 #include "kernels_select.cuh"
 #include "kernels_umma.cuh"
+#include "kernels_umma_ss.cuh"
 #include "kernels_util.cuh"
 
 using namespace b2f;
@@ -181,6 +182,8 @@ struct b2f_index {
   int keep_on_reset = 1;
   int scan_max_auto = 4;  // AUTO: batches up to this size use the SIMT scan
   int profile = 0;
+  int umma_variant = 0;   // 0 auto, 1 smem-stationary queries (SS), 2 TMEM-stationary queries (TS)
+  int l2_prefetch = 1;
   Stats stats;
 };
 
@@ -390,17 +393,34 @@ struct PassPlan {
   int qp;       // max queries per pass
   int C;        // candidate capacity per query
   int64_t n0;   // rows of the dense (bootstrap) phase
-  int S;        // tensor engine: survivor area [0, S) of a list
-  int cap_p;    // tensor engine: private slots per (query, CTA pair) and launch
+  int S;        // TS tensor engine: survivor area [0, S) of a list
+  int cap_p;    // TS tensor engine: private slots per (query, CTA pair) and launch
+  int variant;  // tensor engine variant: 1 = SS (queries in smem), 2 = TS (queries in TMEM)
 };
 
-PassPlan make_plan(const b2f_index* idx, const Shard& S, int path, int k) {
+PassPlan make_plan(const b2f_index* idx, const Shard& S, int path, int k, int64_t nq) {
   PassPlan p;
   p.path = path;
   p.exact = (path == B2F_PATH_SCAN_EXACT);
   p.S = 0;
   p.cap_p = 0;
+  p.variant = 0;
   if (path == B2F_PATH_UMMA_BF16) {
+    // SS: MMA N follows the query count (no padding) but one pass holds <= 192 queries;
+    // TS: 256 queries per pass, MMA M always 256.  AUTO: whichever needs fewer tensor cycles.
+    p.variant = idx->umma_variant;
+    // AUTO = TS.  Measured on B200 (profiles/r01): in isolation TS streams 5.6-5.95 TB/s
+    // vs 5.4 TB/s for SS; under the sustained power cap both settle near 5.0 TB/s (TS becomes
+    // tensor-bound because M is always 256, SS stays short of in-flight bytes).  TS also takes 256
+    // queries per pass and needs no atomics.
+    if (p.variant == 0) p.variant = 2;
+    (void)nq;
+  }
+  if (path == B2F_PATH_UMMA_BF16 && p.variant == 1) {
+    p.qp = kSsMaxQ;
+    p.n0 = static_cast<int64_t>(S.max_pairs) * kSsTileRows;   // one wave of pair tiles
+    p.C = static_cast<int>(round_up(std::max<int64_t>(p.n0, 32ll * k), 256));
+  } else if (path == B2F_PATH_UMMA_BF16) {
     p.qp = kUmmaMaxQ;
     // bootstrap (dense) phase: whole tiles per CTA pair, at least 8k rows (and 4096) in total
     const int64_t wave = static_cast<int64_t>(S.max_pairs) * kTileRows;
@@ -432,7 +452,8 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   cudaStream_t s = S.stream;
   CU_TRY(cudaMemsetAsync(W.cnt, 0, sizeof(int) * nqp, s));
   CU_TRY(cudaMemsetAsync(W.ovf, 0, sizeof(int) * nqp, s));
-  const bool tensor = plan.path == B2F_PATH_UMMA_BF16;
+  const bool tensor = plan.path == B2F_PATH_UMMA_BF16 && plan.variant == 2;   // TS: segmented lists
+  const bool tensor_ss = plan.path == B2F_PATH_UMMA_BF16 && plan.variant == 1;
   if (tensor) CU_TRY(cudaMemsetAsync(W.cnt2, 0, sizeof(int) * nqp * S.max_pairs, s));
   const double u = plan.path == B2F_PATH_UMMA_BF16 ? kUBf16 : kUScan;
   const float two_u = plan.exact ? 0.f : static_cast<float>(2.0 * u * (idx->margin_ppm * 1e-6) * 1.0000001);
@@ -440,7 +461,17 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   st.launches += 1;
 
   int cur = 0;
-  CUtensorMap tmap_p;
+  CUtensorMap tmap_p, tmap_pf, tmap_q;
+  int ss_cols = 0, ss_stages = 0, ss_smem = 0;
+  if (tensor_ss) {
+    ss_cols = static_cast<int>(round_up(nqp, 16));
+    ss_stages = umma_ss_stages(ss_cols);
+    ss_smem = umma_ss_smem_bytes(ss_cols, ss_stages);
+    const uint64_t srows = static_cast<uint64_t>(shadow_rows_padded(N)) * kNumKBlocks;
+    B2F_TRY(make_tmap_bf16(&tmap_p, S.x16, srows, kBlockK, kShadowTileRows));        // one K-block of a 32-row tile
+    B2F_TRY(make_tmap_bf16(&tmap_pf, S.x16, srows, kBlockK, 4 * kShadowTileRows));   // 16 KB prefetch chunks
+    B2F_TRY(make_tmap_bf16(&tmap_q, q16p, static_cast<uint64_t>(ss_cols), kD, static_cast<uint32_t>(ss_cols / 2)));
+  }
   if (tensor) {
     // shadow = [row tiles x 12 K-blocks x tile rows, 64 columns] bf16; box = 128 x 128 B = 16 KB
     B2F_TRY(make_tmap_bf16(&tmap_p, S.x16, static_cast<uint64_t>(shadow_rows_padded(N)) * kNumKBlocks, kBlockK,
@@ -458,7 +489,22 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     else if (plan.exact) end = std::min<int64_t>(N, begin + (C - k));
     else end = std::min<int64_t>(N, begin * std::max(2, idx->growth));
     int n_override = -1;
-    if (plan.path == B2F_PATH_UMMA_BF16) {
+    if (tensor_ss) {
+      const int tb = static_cast<int>(begin / kSsTileRows);
+      const int te = static_cast<int>((end + kSsTileRows - 1) / kSsTileRows);
+      if (end < N) end = static_cast<int64_t>(te) * kSsTileRows;  // phases end on tile boundaries
+      UmmaSsArgs a;
+      a.n_rows = N; a.tile_begin = tb; a.tile_end = te; a.n_cols = ss_cols; a.nq = nqp; a.stages = ss_stages;
+      a.prefetch = idx->l2_prefetch; a.dense = dense ? 1 : 0; a.dense_row0 = 0; a.cand = W.cand[cur]; a.cnt = W.cnt;
+      a.C = C; a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
+      const int pairs = std::min(S.max_pairs, te - tb);
+      {
+        ProfScope ps(idx, S, 0);
+        umma_ss_score_select_kernel<<<2 * pairs, kUmmaThreads, ss_smem, s>>>(tmap_p, tmap_pf, tmap_q, a);
+      }
+      st.score_rows += static_cast<double>(std::min<int64_t>(N, static_cast<int64_t>(te) * kSsTileRows) - begin);
+      if (dense) n_override = (te - tb) * kSsTileRows;
+    } else if (tensor) {
       const int tb = static_cast<int>(begin / kTileRows);
       const int te = static_cast<int>((end + kTileRows - 1) / kTileRows);
       if (end < N) end = static_cast<int64_t>(te) * kTileRows;  // phases end on tile boundaries
@@ -543,7 +589,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
   }
   const int path = resolve_path(idx, S, nq);
   idx->stats.path = path;
-  const PassPlan plan = make_plan(idx, S, path, k);
+  const PassPlan plan = make_plan(idx, S, path, k, nq);
   B2F_TRY(ensure_pass_ws(S, plan.qp, plan.C));
   B2F_TRY(upload_segs(S));
   const int64_t nq_pad = round_up(nq, 16) + kUmmaMaxQ;
@@ -555,6 +601,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
     static bool attr_set[64] = {false};
     if (!attr_set[S.dev & 63]) {
       CU_TRY(cudaFuncSetAttribute(umma_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmemBytes));
+      CU_TRY(cudaFuncSetAttribute(umma_ss_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemLimit));
       attr_set[S.dev & 63] = true;
     }
   } else {
@@ -592,7 +639,7 @@ int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k,
     CU_TRY(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     attr_set3[S.dev & 63] = true;
   }
-  const PassPlan plan = make_plan(idx, S, B2F_PATH_SCAN_EXACT, k);
+  const PassPlan plan = make_plan(idx, S, B2F_PATH_SCAN_EXACT, k, 0);
   B2F_TRY(ensure_pass_ws(S, plan.qp, plan.C));
   cudaStream_t s = S.stream;
   for (size_t b0 = 0; b0 < bad.size(); b0 += kScanMaxQ) {
@@ -954,6 +1001,11 @@ int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
     idx->margin_ppm = value;
   } else if (k == "keep_on_reset") {
     idx->keep_on_reset = value ? 1 : 0;
+  } else if (k == "umma_variant") {
+    if (value < 0 || value > 2) return fail(B2F_ERR_INVALID, "umma_variant must be 0 (auto), 1 (SS) or 2 (TS)");
+    idx->umma_variant = static_cast<int>(value);
+  } else if (k == "l2_prefetch") {
+    idx->l2_prefetch = value ? 1 : 0;
   } else if (k == "profile") {
     idx->profile = value ? 1 : 0;
   } else if (k == "scan_max_auto") {

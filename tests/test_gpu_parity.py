@@ -17,13 +17,16 @@ from oracle import c_oracle, flat_ip
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PATHS = ["scan_f32", "scan_exact", "umma_bf16"]
+PATHS = ["scan_f32", "scan_exact", "umma_ss", "umma_ts"]   # umma_*: the two tensor-engine variants
 RTOL = 1e-5          # the tolerance north_star states
 RTOL_TRUTH = 1e-6    # what the exact rescoring actually delivers vs float64
 
 
 def make_index(path, P=None, devices=None, **opts):
     idx = FlatIPIndex(768, devices=devices)
+    if path in ("umma_ss", "umma_ts"):
+        idx.set_option("umma_variant", 1 if path == "umma_ss" else 2)
+        path = "umma_bf16"
     idx.set_option("path", path)
     for k, v in opts.items():
         idx.set_option(k, v)
@@ -64,7 +67,7 @@ def test_config1_100k_173q_top100(path, c1_data):
     r = check_against_oracle(D, I, P, Q, 100)
     assert r["exact_rows"] >= 170
     assert idx.stat("fallback_queries") == 0
-    assert int(idx.stat("path")) == {"scan_f32": 1, "scan_exact": 2, "umma_bf16": 3}[path]
+    assert int(idx.stat("path")) == {"scan_f32": 1, "scan_exact": 2, "umma_ss": 3, "umma_ts": 3}[path]
     assert idx.stat("launches") > 0
 
 
@@ -79,7 +82,7 @@ def test_results_are_bitwise_path_independent(path, c1_data):
     np.testing.assert_array_equal(D, D0)
 
 
-@pytest.mark.parametrize("path", ["scan_f32", "umma_bf16"])
+@pytest.mark.parametrize("path", ["scan_f32", "umma_ss", "umma_ts"])
 def test_top1000_selection_pressure(path, c1_data):
     P, Q = c1_data  # BASELINE config 2's k = 1000 (gen_ranking_data.py negatives), reduced rows
     idx = make_index(path, P)
