@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--growth", type=int, default=0, help="phase growth factor override (0 = engine default)")
     ap.add_argument("--variant", type=int, default=0, help="tensor engine variant: 0 auto, 1 SS, 2 TS")
     ap.add_argument("--l2-prefetch", type=int, default=1)
+    ap.add_argument("--tighten", type=int, default=-1, help="-1 engine default, 0 off, >0 refresher pause in ns")
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
@@ -215,6 +216,8 @@ def run_b2f_arm(args):
         index.set_option("growth", args.growth)
     index.set_option("umma_variant", args.variant)
     index.set_option("l2_prefetch", args.l2_prefetch)
+    if args.tighten >= 0:
+        index.set_option("tighten", args.tighten)
     sharded = ShardedFlatIP(index=index)
     t0 = time.perf_counter()
     lo, hi = sharded.add_synthetic(args.rows, seed=0, stream=0)

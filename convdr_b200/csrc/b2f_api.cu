@@ -101,6 +101,7 @@ struct Workspace {
   int* ovf = nullptr;
   float* margin = nullptr;
   int* err = nullptr;
+  bool areas_clean = false;   // tensor-engine invariant: private areas of both cand buffers are all-zero
   uint64_t* gath = nullptr;   // refresh scratch: dense copy of a segmented list
   int* cnt2 = nullptr;        // [qp][max_pairs] per-pair append counts of the tensor engine
   // queries of one search
@@ -184,6 +185,10 @@ struct b2f_index {
   int profile = 0;
   int umma_variant = 0;   // 0 auto, 1 smem-stationary queries (SS), 2 TMEM-stationary queries (TS)
   int l2_prefetch = 1;
+  int tighten = 0;        // TS engine: in-kernel threshold tightening (one launch after the bootstrap);
+                          // pause of the refresher between rounds in ns, 0 = off (geometric phases).
+                          // Off by default: same-box A/B on B200 shows 1.85 vs 1.74 ms/step at 4.8 M rows
+                          // and no gain at 38.6 M rows.
   Stats stats;
 };
 
@@ -324,6 +329,7 @@ int ensure_pass_ws(Shard& S, int qp, int C) {
   }
   W.qp_cap = qp;
   W.C = C;
+  W.areas_clean = false;
   return B2F_OK;
 }
 
@@ -428,8 +434,9 @@ PassPlan make_plan(const b2f_index* idx, const Shard& S, int path, int k, int64_
     p.n0 = t0 * wave;
     p.S = static_cast<int>(round_up(std::max(1024, 4 * k), 256));
     // expected appends per (query, pair) in a phase: 2 (margin) * (growth-1) * k / pairs; x2 safety
+    // (with in-kernel tightening the pass rate follows k/rows_seen, far fewer appends; keep the bound)
     const int64_t expect = 4ll * (std::max(2, idx->growth) - 1) * k / S.max_pairs;
-    p.cap_p = static_cast<int>(round_up(std::max<int64_t>(std::max<int64_t>(256, t0 * kTileRows), expect), 32));
+    p.cap_p = static_cast<int>(round_up(std::max<int64_t>(std::max<int64_t>(512, t0 * kTileRows), expect), 32));
     p.C = p.S + S.max_pairs * p.cap_p;
   } else {
     p.qp = kScanMaxQ;
@@ -454,7 +461,16 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   CU_TRY(cudaMemsetAsync(W.ovf, 0, sizeof(int) * nqp, s));
   const bool tensor = plan.path == B2F_PATH_UMMA_BF16 && plan.variant == 2;   // TS: segmented lists
   const bool tensor_ss = plan.path == B2F_PATH_UMMA_BF16 && plan.variant == 1;
-  if (tensor) CU_TRY(cudaMemsetAsync(W.cnt2, 0, sizeof(int) * nqp * S.max_pairs, s));
+  if (tensor) {
+    CU_TRY(cudaMemsetAsync(W.cnt2, 0, sizeof(int) * nqp * S.max_pairs, s));
+    if (!W.areas_clean) {   // only after (re)allocation or after another engine used the lists
+      CU_TRY(cudaMemsetAsync(W.cand[0], 0, sizeof(uint64_t) * static_cast<size_t>(W.qp_cap) * W.C, s));
+      CU_TRY(cudaMemsetAsync(W.cand[1], 0, sizeof(uint64_t) * static_cast<size_t>(W.qp_cap) * W.C, s));
+      W.areas_clean = true;
+    }
+  } else {
+    W.areas_clean = false;  // flat lists overwrite the private areas
+  }
   const double u = plan.path == B2F_PATH_UMMA_BF16 ? kUBf16 : kUScan;
   const float two_u = plan.exact ? 0.f : static_cast<float>(2.0 * u * (idx->margin_ppm * 1e-6) * 1.0000001);
   margin_kernel<<<(nqp + 127) / 128, 128, 0, s>>>(qnormp, S.maxnorm2, two_u, nqp, W.margin);
@@ -487,6 +503,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     const bool dense = (phase == 0);
     if (dense) end = std::min<int64_t>(N, plan.n0);
     else if (plan.exact) end = std::min<int64_t>(N, begin + (C - k));
+    else if (tensor && idx->tighten) end = N;   // thresholds are tightened inside the kernel
     else end = std::min<int64_t>(N, begin * std::max(2, idx->growth));
     int n_override = -1;
     if (tensor_ss) {
@@ -512,6 +529,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       a.n_rows = N; a.tile_begin = tb; a.tile_end = te; a.nq = nqp; a.q16 = q16p;
       a.dense = dense ? 1 : 0; a.cand = W.cand[cur]; a.C = C; a.S = plan.S; a.cap_p = plan.cap_p;
       a.max_pairs = S.max_pairs; a.cnt2 = W.cnt2; a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
+      a.tighten = idx->tighten; a.k = k; a.margin = W.margin; a.surv_cnt = W.cnt;
       const int pairs = std::min(S.max_pairs, te - tb);
       {
         ProfScope ps(idx, S, 0);
@@ -1006,6 +1024,9 @@ int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
     idx->umma_variant = static_cast<int>(value);
   } else if (k == "l2_prefetch") {
     idx->l2_prefetch = value ? 1 : 0;
+  } else if (k == "tighten") {
+    if (value < 0 || value > 1000000) return fail(B2F_ERR_INVALID, "tighten must be 0 (off) or a pause in ns <= 1e6");
+    idx->tighten = static_cast<int>(value);
   } else if (k == "profile") {
     idx->profile = value ? 1 : 0;
   } else if (k == "scan_max_auto") {

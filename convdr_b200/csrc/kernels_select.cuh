@@ -109,9 +109,9 @@ __device__ int block_compact(const uint64_t* __restrict__ in, int n, uint64_t T,
 }
 
 // Gather the valid entries of a segmented candidate list (survivors [0,m) + one private area per
-// CTA pair, see kernels_umma.cuh UmmaArgs) into a dense array; returns the entry count and clears
-// the per-pair counters for the next launch.
-__device__ int block_gather_segments(const uint64_t* __restrict__ in, int m, int S, int cap_p, int max_pairs,
+// CTA pair, see kernels_umma.cuh UmmaArgs) into a dense array; returns the entry count, zeroes the
+// consumed private slots and clears the per-pair counters for the next launch.
+__device__ int block_gather_segments(uint64_t* __restrict__ in, int m, int S, int cap_p, int max_pairs,
                                      int* __restrict__ cnt2q, uint64_t* __restrict__ gath, SelectSmem& sm,
                                      int* seg_off /* smem [max_pairs] */) {
   for (int i = threadIdx.x; i < m; i += kSelThreads) gath[i] = in[i];
@@ -129,9 +129,12 @@ __device__ int block_gather_segments(const uint64_t* __restrict__ in, int m, int
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int p = warp; p < max_pairs; p += kSelThreads / 32) {
     const int c = (p + 1 < max_pairs ? seg_off[p + 1] : total) - seg_off[p];
-    const uint64_t* src = in + S + static_cast<int64_t>(p) * cap_p;
+    uint64_t* src = in + S + static_cast<int64_t>(p) * cap_p;
     uint64_t* dst = gath + m + seg_off[p];
-    for (int e = lane; e < c; e += 32) dst[e] = src[e];
+    for (int e = lane; e < c; e += 32) {
+      dst[e] = src[e];
+      src[e] = 0ull;   // invariant of the tensor engine: private areas are all-zero between launches
+    }
   }
   __syncthreads();
   for (int p = threadIdx.x; p < max_pairs; p += kSelThreads) cnt2q[p] = 0;
@@ -146,7 +149,7 @@ __device__ int block_gather_segments(const uint64_t* __restrict__ in, int m, int
 //   exact mode: scores are final; tauP = the k-th largest record, survivors are exactly the top k.
 // With fewer than k valid records nothing can be rejected yet (tau = -inf / tauP = 0).
 __global__ void __launch_bounds__(kSelThreads) refresh_kernel(
-    const uint64_t* __restrict__ cand_in, uint64_t* __restrict__ cand_out, uint64_t* __restrict__ gath,
+    uint64_t* __restrict__ cand_in, uint64_t* __restrict__ cand_out, uint64_t* __restrict__ gath,
     int* __restrict__ cnt, int C, int k, int exact, const float* __restrict__ margin,
     float* __restrict__ tau, uint64_t* __restrict__ tauP, int n_override, int S, int cap_p, int max_pairs,
     int* __restrict__ cnt2, int* __restrict__ ovf) {
@@ -159,7 +162,8 @@ __global__ void __launch_bounds__(kSelThreads) refresh_kernel(
   int limit = C;
   if (max_pairs > 0) {   // segmented list written by the tensor engine
     uint64_t* g = gath + static_cast<int64_t>(q) * C;
-    n = block_gather_segments(in, min(cnt[q], S), S, cap_p, max_pairs, cnt2 + q * max_pairs, g, sm, seg_off);
+    n = block_gather_segments(cand_in + static_cast<int64_t>(q) * C, min(cnt[q], S), S, cap_p, max_pairs,
+                              cnt2 + q * max_pairs, g, sm, seg_off);
     in = g;
     limit = S;
   } else {

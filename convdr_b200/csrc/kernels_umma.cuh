@@ -39,7 +39,7 @@ constexpr int kTmemCols = 512;
 constexpr int kTmemColsA = kD / 2;             // 384 columns: 128 lanes x 768 bf16
 constexpr int kTmemColD = kTmemColsA;          // accumulators: columns [384, 512)
 constexpr int kAccStages = (kTmemCols - kTmemColsA) / kTileRows;    // 2 (double-buffered)
-constexpr int kUmmaTailBytes = 1024;           // barriers + tmem pointer
+constexpr int kUmmaTailBytes = 2048;           // barriers, tmem pointer, refresher histogram
 constexpr int kUmmaSmemBytes = kNumStages * kStageBytes + kUmmaTailBytes + 1024;  // + alignment slack
 static_assert(kUmmaSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
 static_assert(kAccStages >= 1 && kAccStages <= 2, "TMEM budget: 384 query columns + accumulators in 128 columns");
@@ -57,9 +57,15 @@ struct UmmaArgs {
   uint64_t* cand;
   int C, S, cap_p, max_pairs;
   int* cnt2;                  // [nq][max_pairs] entries written by each pair in this launch
-  const float* tau;           // [nq]
+  float* tau;                 // [nq] thresholds (raised in-kernel when tighten != 0)
   int* ovf;                   // [nq] set when a private area was too small
   int* err;                   // device error flag (barrier timeout)
+  // in-kernel threshold tightening (see the refresher role below)
+  int tighten;                // >0: the idle warp of each CTA keeps re-selecting tau while the stream runs;
+                              //     the value is the pause between rounds in ns
+  int k;
+  const float* margin;        // [nq] 2*eps of the prefilter
+  const int* surv_cnt;        // [nq] valid survivors in [0, S)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -250,6 +256,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
   const uint32_t bar_tfull = bar_qready + 8;                      // [2]
   const uint32_t bar_tempty = bar_tfull + 16;                     // [2]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(base_ptr + kNumStages * kStageBytes + 16 * kNumStages + 40);
+  volatile int* epi_done_s = reinterpret_cast<volatile int*>(tmem_ptr_s + 1);     // epilogue warps that finished
+  unsigned int* hist_s = reinterpret_cast<unsigned int*>(base_ptr + kNumStages * kStageBytes + 512);  // [256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -258,6 +266,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
   const int npairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) prefetch_tmap(&tmap_p);
+  if (warp == 3 && lane == 0) *epi_done_s = 0;
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kNumStages; ++s) {
       mbar_init(bar_full + 8 * s, 2);   // leader's expect_tx arrive + peer's remote arrive
@@ -354,15 +363,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(bar_qready, 0));
     }
-    const float tau = (q_ok && !a.dense) ? a.tau[q] : INFINITY;
+    float tau = (q_ok && !a.dense) ? a.tau[q] : INFINITY;
+    volatile float* tau_g = a.tau + (q_ok ? q : 0);
+    volatile int* my_cnt = a.cnt2 + (q_ok ? q : 0) * a.max_pairs + pair;
+    const bool live = a.tighten && q_ok && !a.dense;
+    int n_pub = 0;    // entries already published to the refresher
     uint64_t* my_list = a.cand + static_cast<int64_t>(q_ok ? q : 0) * a.C + a.S + static_cast<int64_t>(pair) * a.cap_p;
     int n_mine = 0;   // entries this thread appended for (query q, this pair)
     const uint32_t tempty_leader = mapa_u32(bar_tempty, 0);
     int it = 0;
     for (int tile = a.tile_begin + pair; tile < a.tile_end; tile += npairs, ++it) {
       const uint32_t as = static_cast<uint32_t>(it) % kAccStages, aph = (static_cast<uint32_t>(it) / kAccStages) & 1u;
+      float tau_new = tau;
+      if (live) tau_new = *tau_g;            // issued before the wait: the L2 latency hides behind it
       mbar_wait(bar_tfull + 8 * as, aph, a.err);
       tc_fence_after();
+      tau = fmaxf(tau, tau_new);             // thresholds only rise
       uint32_t v[kTileRows];
 #pragma unroll
       for (int w = 0; w < kTileRows / 32; ++w) tmem_ld_x32(lane_addr + kTmemColD + as * kTileRows + 32 * w, v + 32 * w);
@@ -394,14 +410,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
           for (int c = 0; c < 32; ++c) m |= (__uint_as_float(v[32 * w + c]) >= tau) ? (1u << c) : 0u;
           if (32 * w + 32 > n_valid) m &= (n_valid > 32 * w) ? ((1u << (n_valid - 32 * w)) - 1u) : 0u;  // shard tail
           uint32_t any = __reduce_or_sync(0xffffffffu, m);
-          while (any) {   // rare
-            const int c = __ffs(any) - 1;
-            any &= any - 1;
-            const uint32_t bits = tmem_ld_x1(lane_addr + kTmemColD + as * kTileRows + 32 * w + c);
-            tmem_ld_wait();
-            if ((m >> c) & 1u) {   // no atomics: the area is private to this thread
-              if (n_mine < a.cap_p) my_list[n_mine] = pack_cand(__uint_as_float(bits), static_cast<uint32_t>(row0 + 32 * w + c));
-              ++n_mine;
+          if (__popc(any) > 6) {
+            // Busy word (loose threshold, early in a pass): fully unrolled predicated stores — ~9
+            // instructions per column whether it hits or not, but no TMEM round trip per hit column.
+            if (m) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                if ((m >> c) & 1u) {
+                  const int slot = n_mine + __popc(m & ((1u << c) - 1u));
+                  if (slot < a.cap_p)
+                    my_list[slot] = pack_cand(__uint_as_float(v[32 * w + c]), static_cast<uint32_t>(row0 + 32 * w + c));
+                }
+              }
+              n_mine += __popc(m);
+            }
+          } else {
+            while (any) {   // rare: re-read the flagged column from TMEM (v[] must stay in registers)
+              const int c = __ffs(any) - 1;
+              any &= any - 1;
+              const uint32_t bits = tmem_ld_x1(lane_addr + kTmemColD + as * kTileRows + 32 * w + c);
+              tmem_ld_wait();
+              if ((m >> c) & 1u) {   // no atomics: the area is private to this thread
+                if (n_mine < a.cap_p) my_list[n_mine] = pack_cand(__uint_as_float(bits), static_cast<uint32_t>(row0 + 32 * w + c));
+                ++n_mine;
+              }
             }
           }
         }
@@ -409,10 +441,129 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * as);   // this accumulator stage is free again
+      if (live && n_mine != n_pub) {
+        // Publish the new entries to the refresher.  No fence (a MEMBAR.GPU per tile would dominate):
+        // private areas are all-zero before the launch and a record is one 8-byte store, so a slot
+        // the refresher reads ahead of its store is 0 and is skipped.
+        *my_cnt = min(n_mine, a.cap_p);
+        n_pub = n_mine;
+      }
     }
     if (q_ok) {
-      a.cnt2[q * a.max_pairs + pair] = min(n_mine, a.cap_p);
+      *my_cnt = min(n_mine, a.cap_p);
       if (n_mine > a.cap_p) a.ovf[q] = 1;
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(const_cast<int*>(epi_done_s), 1);
+  } else if (warp == 3 && a.tighten && !a.dense) {
+    // ===================== refresher: in-kernel threshold tightening =====================
+    // While the stream runs, this otherwise idle warp keeps recomputing, for the queries assigned
+    // to this CTA, the k-th best approximate score among everything published so far (survivors of
+    // the bootstrap + every pair's private area) and raises tau[q] = kth - 2*eps.  Any subset of the
+    // rows seen gives a valid (lower) bound, so no synchronisation with the writers is needed: slots
+    // not yet written read as 0 (the areas are zero before the launch) and are skipped.  Effect: the pass rate follows k/rows_seen
+    // continuously instead of per launch, so one launch covers the whole shard.
+    const int nseg = a.max_pairs;
+    int last_total[4] = {-1, -1, -1, -1};
+    while (*epi_done_s < 4) {
+      int qi = 0;
+      for (int q = blockIdx.x; q < a.nq; q += gridDim.x, ++qi) {
+        const uint64_t* list = a.cand + static_cast<int64_t>(q) * a.C;
+        const volatile int* cnts = a.cnt2 + q * a.max_pairs;
+        const int m = min(a.surv_cnt[q], a.S);
+        // segment lengths owned by this lane (segment s = lane, lane+32, ...; s == nseg: survivors)
+        int total = 0;
+        int len[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int sgm = lane + 32 * j;
+          len[j] = (sgm < nseg) ? cnts[sgm] : 0;
+          total += len[j];
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        total += m;
+        if (total < a.k || (qi < 4 && total == last_total[qi])) continue;   // nothing new since last time
+        if (qi < 4) last_total[qi] = total;
+        uint32_t prefix = 0, mask = 0;
+        unsigned int remaining = static_cast<unsigned int>(a.k);
+        for (int pass = 0; pass < 4; ++pass) {   // radix select on the 32-bit score key
+          const int shift = 24 - 8 * pass;
+#pragma unroll
+          for (int b = 0; b < 8; ++b) hist_s[lane + 32 * b] = 0;
+          __syncwarp();
+          // survivors of the bootstrap: 4 independent loads per lane and round
+          for (int i0 = 0; i0 < m; i0 += 128) {
+            uint32_t key[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = i0 + 32 * u + lane;
+              key[u] = (i < m) ? static_cast<uint32_t>(__ldcg(list + i) >> 32) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (key[u] != 0u && (key[u] & mask) == prefix) atomicAdd(&hist_s[(key[u] >> shift) & 255u], 1u);
+          }
+          // private areas: 8 segments per round, lane e reads entry e of each (loads are independent,
+          // so one L2 latency covers the round instead of one per entry)
+          for (int s0 = 0; s0 < nseg; s0 += 8) {
+            int L[8], maxlen = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int sg = s0 + u, j = sg >> 5;
+              const int mine = (j == 0) ? len[0] : (j == 1) ? len[1] : (j == 2) ? len[2] : len[3];
+              L[u] = __shfl_sync(0xffffffffu, mine, sg & 31);
+              if (sg >= nseg) L[u] = 0;
+              maxlen = max(maxlen, L[u]);
+            }
+            for (int e0 = 0; e0 < maxlen; e0 += 32) {
+              uint32_t key[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int e = e0 + lane;
+                key[u] = (e < L[u]) ? static_cast<uint32_t>(__ldcg(list + a.S + static_cast<int64_t>(s0 + u) * a.cap_p + e) >> 32) : 0u;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (key[u] != 0u && (key[u] & mask) == prefix) atomicAdd(&hist_s[(key[u] >> shift) & 255u], 1u);
+            }
+          }
+          __syncwarp();
+          // lane l owns buckets 255-8l .. 248-8l (descending); find the bucket holding the `remaining`-th
+          unsigned int h[8], sum = 0;
+#pragma unroll
+          for (int b = 0; b < 8; ++b) { h[b] = hist_s[255 - (8 * lane + b)]; sum += h[b]; }
+          unsigned int inc = sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          unsigned int before = inc - sum;   // keys in higher buckets owned by lower lanes
+          int digit = -1;
+          unsigned int rem_new = 0;
+          if (inc >= remaining && before < remaining) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+              if (digit < 0 && before + h[b] >= remaining) { digit = 255 - (8 * lane + b); rem_new = remaining - before; }
+              before += h[b];
+            }
+          }
+          const unsigned int who = __ballot_sync(0xffffffffu, digit >= 0);
+          if (who == 0u) { prefix = 0; break; }   // cannot happen (total >= k); never publish a bogus bound
+          const int src = __ffs(who) - 1;
+          digit = __shfl_sync(0xffffffffu, digit, src);
+          remaining = __shfl_sync(0xffffffffu, rem_new, src);
+          prefix |= static_cast<uint32_t>(digit) << shift;
+          mask |= 0xffu << shift;
+          __syncwarp();
+        }
+        if (lane == 0 && prefix != 0u) {
+          const float t = __fsub_rd(key2f(prefix), a.margin[q]);
+          if (t > a.tau[q]) *reinterpret_cast<volatile float*>(a.tau + q) = t;
+        }
+      }
+      __nanosleep(static_cast<unsigned int>(a.tighten));
     }
   }
   __syncwarp();

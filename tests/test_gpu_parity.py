@@ -307,6 +307,18 @@ def test_device_resident_search_and_merge_kernel():
     np.testing.assert_array_equal(Dm.cpu().numpy(), Dh)
 
 
+def test_in_kernel_threshold_tightening_gives_identical_results(c1_data):
+    P, Q = c1_data
+    base = make_index("umma_ts", P)
+    D0, I0 = base.search(Q, 100)
+    tight = make_index("umma_ts", P, tighten=2000)
+    D1, I1 = tight.search(Q, 100)
+    np.testing.assert_array_equal(I1, I0)
+    np.testing.assert_array_equal(D1, D0)
+    assert tight.stat("fallback_queries") == 0
+    assert tight.stat("phases") < base.stat("phases")     # bootstrap + one launch
+
+
 def test_auto_policy_and_invalid_arguments():
     P = c_oracle.synth_block(0, 20000, seed=13)
     idx = make_index("auto", P)

@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:umma_score -s 8 -c 1 -o gpurun_out/prof_umma python bench.py --rows 4829565 --steps 2 --warmup 3 --no-cpu-baseline --no-check > gpurun_out/ncu_full.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_full.log
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:umma_score -s 7 -c 1 -o gpurun_out/prof_umma python bench.py --rows 4829565 --steps 2 --warmup 3 --no-cpu-baseline --no-check > gpurun_out/ncu_full.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_full.log
