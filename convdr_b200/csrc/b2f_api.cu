@@ -104,6 +104,9 @@ struct Workspace {
   bool areas_clean = false;   // tensor-engine invariant: private areas of both cand buffers are all-zero
   uint64_t* gath = nullptr;   // refresh scratch: dense copy of a segmented list
   int* cnt2 = nullptr;        // [qp][max_pairs] per-pair append counts of the tensor engine
+  unsigned int* hist = nullptr;   // [qp][kHistBuckets] tightening histogram of the tensor engine
+  uint32_t* hkey0 = nullptr;      // [qp] its base key
+  int* hshift = nullptr;          // [qp] log2(keys per bucket)
   // queries of one search
   int64_t nq_cap = 0;
   float* q32 = nullptr;
@@ -185,10 +188,9 @@ struct b2f_index {
   int profile = 0;
   int umma_variant = 0;   // 0 auto, 1 smem-stationary queries (SS), 2 TMEM-stationary queries (TS)
   int l2_prefetch = 1;
-  int tighten = 0;        // TS engine: in-kernel threshold tightening (one launch after the bootstrap);
-                          // pause of the refresher between rounds in ns, 0 = off (geometric phases).
-                          // Off by default: same-box A/B on B200 shows 1.85 vs 1.74 ms/step at 4.8 M rows
-                          // and no gain at 38.6 M rows.
+  int tighten = 400;      // TS engine: in-kernel threshold tightening through a global hit histogram (one
+                          // launch after the bootstrap); pause of the refresher between rounds in ns,
+                          // 0 = off (geometric phases with a refresh kernel between them).
   Stats stats;
 };
 
@@ -282,14 +284,16 @@ int ingest_rows(b2f_index* idx, Shard& S, int64_t n) {
 int ensure_query_ws(Shard& S, int64_t nq, int k) {
   Workspace& W = S.ws;
   if (nq > W.nq_cap) {
-    dev_free(W.q32); dev_free(W.q16); dev_free(W.qnorm); dev_free(W.ovf_all);
-    if (W.ovf_host) { cudaFreeHost(W.ovf_host); W.ovf_host = nullptr; }
+    dev_free(W.q32); dev_free(W.q16); dev_free(W.qnorm);
+    if (W.ovf_host) { cudaFreeHost(W.ovf_host); W.ovf_host = nullptr; W.ovf_all = nullptr; }
     const int64_t cap = std::max<int64_t>(nq, 256);
     B2F_TRY(dev_alloc(&W.q32, static_cast<size_t>(cap) * kD));
     B2F_TRY(dev_alloc(&W.q16, static_cast<size_t>(cap + kUmmaMaxQ + 16) * kD));
     B2F_TRY(dev_alloc(&W.qnorm, static_cast<size_t>(cap + kUmmaMaxQ + 16)));
-    B2F_TRY(dev_alloc(&W.ovf_all, static_cast<size_t>(cap)));
-    CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&W.ovf_host), static_cast<size_t>(cap) * sizeof(int)));
+    // per-query overflow flags live in mapped pinned host memory: the last kernel of a pass writes them
+    // straight to the host (no copy operation on the stream), the host reads them after the sync
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&W.ovf_host), static_cast<size_t>(cap) * sizeof(int), cudaHostAllocMapped));
+    CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&W.ovf_all), W.ovf_host, 0));
     W.nq_cap = cap;
   }
   const int64_t need_out = nq * k;
@@ -314,8 +318,12 @@ int ensure_pass_ws(Shard& S, int qp, int C) {
   C = std::max(C, W.C);
   dev_free(W.cand[0]); dev_free(W.cand[1]); dev_free(W.cnt); dev_free(W.tau); dev_free(W.tauP);
   dev_free(W.ovf); dev_free(W.margin); dev_free(W.gath); dev_free(W.cnt2);
+  dev_free(W.hist); dev_free(W.hkey0); dev_free(W.hshift);
   B2F_TRY(dev_alloc(&W.gath, static_cast<size_t>(qp) * C));
   B2F_TRY(dev_alloc(&W.cnt2, static_cast<size_t>(qp) * 128));
+  B2F_TRY(dev_alloc(&W.hist, static_cast<size_t>(qp) * kHistBuckets));
+  B2F_TRY(dev_alloc(&W.hkey0, static_cast<size_t>(qp)));
+  B2F_TRY(dev_alloc(&W.hshift, static_cast<size_t>(qp)));
   B2F_TRY(dev_alloc(&W.cand[0], static_cast<size_t>(qp) * C));
   B2F_TRY(dev_alloc(&W.cand[1], static_cast<size_t>(qp) * C));
   B2F_TRY(dev_alloc(&W.cnt, static_cast<size_t>(qp)));
@@ -344,12 +352,20 @@ int ensure_pin(Shard& S, size_t bytes) {
   return B2F_OK;
 }
 
-__global__ void margin_kernel(const float* __restrict__ qnorm, const unsigned int* __restrict__ maxnorm2_bits,
-                              float two_u, int nq, float* __restrict__ margin) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq) return;
-  const float pn = __fsqrt_ru(__uint_as_float(*maxnorm2_bits));
-  margin[q] = __fmul_ru(__fmul_ru(qnorm[q], pn), two_u);
+// Start of a pass, one block per query: the prefilter margin 2*eps_q = 2u * ||q|| * max||p|| (rounded
+// up) and the zeroing of the pass state (one launch instead of three memsets and a kernel).
+__global__ void pass_init_kernel(const float* __restrict__ qnorm, const unsigned int* __restrict__ maxnorm2_bits,
+                                 float two_u, float* __restrict__ margin, int* __restrict__ cnt,
+                                 int* __restrict__ ovf, int* __restrict__ cnt2, int max_pairs) {
+  const int q = blockIdx.x;
+  if (threadIdx.x == 0) {
+    const float pn = __fsqrt_ru(__uint_as_float(*maxnorm2_bits));
+    margin[q] = __fmul_ru(__fmul_ru(qnorm[q], pn), two_u);
+    cnt[q] = 0;
+    ovf[q] = 0;
+  }
+  if (cnt2 != nullptr)
+    for (int p = threadIdx.x; p < max_pairs; p += blockDim.x) cnt2[q * max_pairs + p] = 0;
 }
 
 __global__ void fill_pad_kernel(float* D, int64_t* I, int64_t n) {
@@ -457,12 +473,9 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   const int64_t N = S.n;
   const int C = W.C;
   cudaStream_t s = S.stream;
-  CU_TRY(cudaMemsetAsync(W.cnt, 0, sizeof(int) * nqp, s));
-  CU_TRY(cudaMemsetAsync(W.ovf, 0, sizeof(int) * nqp, s));
   const bool tensor = plan.path == B2F_PATH_UMMA_BF16 && plan.variant == 2;   // TS: segmented lists
   const bool tensor_ss = plan.path == B2F_PATH_UMMA_BF16 && plan.variant == 1;
   if (tensor) {
-    CU_TRY(cudaMemsetAsync(W.cnt2, 0, sizeof(int) * nqp * S.max_pairs, s));
     if (!W.areas_clean) {   // only after (re)allocation or after another engine used the lists
       CU_TRY(cudaMemsetAsync(W.cand[0], 0, sizeof(uint64_t) * static_cast<size_t>(W.qp_cap) * W.C, s));
       CU_TRY(cudaMemsetAsync(W.cand[1], 0, sizeof(uint64_t) * static_cast<size_t>(W.qp_cap) * W.C, s));
@@ -473,7 +486,8 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   }
   const double u = plan.path == B2F_PATH_UMMA_BF16 ? kUBf16 : kUScan;
   const float two_u = plan.exact ? 0.f : static_cast<float>(2.0 * u * (idx->margin_ppm * 1e-6) * 1.0000001);
-  margin_kernel<<<(nqp + 127) / 128, 128, 0, s>>>(qnormp, S.maxnorm2, two_u, nqp, W.margin);
+  pass_init_kernel<<<nqp, 128, 0, s>>>(qnormp, S.maxnorm2, two_u, W.margin, W.cnt, W.ovf,
+                                       tensor ? W.cnt2 : nullptr, S.max_pairs);
   st.launches += 1;
 
   int cur = 0;
@@ -529,7 +543,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       a.n_rows = N; a.tile_begin = tb; a.tile_end = te; a.nq = nqp; a.q16 = q16p;
       a.dense = dense ? 1 : 0; a.cand = W.cand[cur]; a.C = C; a.S = plan.S; a.cap_p = plan.cap_p;
       a.max_pairs = S.max_pairs; a.cnt2 = W.cnt2; a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
-      a.tighten = idx->tighten; a.k = k; a.margin = W.margin; a.surv_cnt = W.cnt;
+      a.tighten = idx->tighten; a.k = k; a.margin = W.margin; a.hist = W.hist; a.hkey0 = W.hkey0; a.hshift = W.hshift;
       const int pairs = std::min(S.max_pairs, te - tb);
       {
         ProfScope ps(idx, S, 0);
@@ -553,11 +567,19 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       if (dense) n_override = static_cast<int>(end - begin);
     }
     CU_TRY(cudaGetLastError());
+    if (tensor && end >= N) {   // the last refresh of a TS pass is part of finalize_kernel
+      st.launches += 1;
+      st.phases += 1;
+      begin = end;
+      ++phase;
+      break;
+    }
     {
       ProfScope ps(idx, S, 1);
       refresh_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.gath, W.cnt, C, k, plan.exact ? 1 : 0,
                                                 W.margin, W.tau, W.tauP, n_override, plan.S, plan.cap_p,
-                                                tensor ? S.max_pairs : 0, W.cnt2, W.ovf);
+                                                tensor ? S.max_pairs : 0, W.cnt2, W.ovf,
+                                                (tensor && idx->tighten && end < N) ? W.hist : nullptr, W.hkey0, W.hshift);
     }
     CU_TRY(cudaGetLastError());
     cur ^= 1;
@@ -565,6 +587,18 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     st.phases += 1;
     begin = end;
     ++phase;
+  }
+  if (tensor) {
+    ProfScope ps(idx, S, 1);
+    int P = 4096;
+    while (P < plan.S) P <<= 1;
+    finalize_kernel<<<nqp, kFinThreads, static_cast<size_t>(2) * P * sizeof(uint64_t), s>>>(
+        W.cand[cur], W.gath, W.cnt, C, k, W.margin, plan.S, plan.cap_p, S.max_pairs, W.cnt2, W.ovf, ovf_dst, q32p,
+        S.x32, S.segs_d, static_cast<int>(S.segs.size()), S.has_ids ? S.idmap : nullptr, D_out, I_out, out_stride, P);
+    CU_TRY(cudaGetLastError());
+    st.launches += 1;
+    st.passes += 1;
+    return B2F_OK;
   }
   {
     ProfScope ps(idx, S, 1);
@@ -580,7 +614,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   CU_TRY(cudaGetLastError());
   st.launches += 1;
   st.passes += 1;
-  if (ovf_dst) CU_TRY(cudaMemcpyAsync(ovf_dst, W.ovf, sizeof(int) * nqp, cudaMemcpyDeviceToDevice, s));
+  if (ovf_dst) CU_TRY(cudaMemcpyAsync(ovf_dst, W.ovf, sizeof(int) * nqp, cudaMemcpyDefault, s));
   return B2F_OK;
 }
 
@@ -602,7 +636,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
   if (S.n == 0) {
     fill_pad_kernel<<<static_cast<int>((nq * k + 255) / 256), 256, 0, s>>>(D_d, I_d, nq * k);
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemsetAsync(W.ovf_all, 0, sizeof(int) * nq, s));
+    std::memset(W.ovf_host, 0, sizeof(int) * nq);   // no kernel writes the flags of an empty shard
     return B2F_OK;
   }
   const int path = resolve_path(idx, S, nq);
@@ -620,6 +654,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
     if (!attr_set[S.dev & 63]) {
       CU_TRY(cudaFuncSetAttribute(umma_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmemBytes));
       CU_TRY(cudaFuncSetAttribute(umma_ss_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemLimit));
+      CU_TRY(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 8));
       attr_set[S.dev & 63] = true;
     }
   } else {
@@ -635,7 +670,6 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
     B2F_TRY(enqueue_pass(idx, S, plan, q_d + q0 * kD, W.q16 + q0 * kD, W.qnorm + q0, nqp, k, D_d + q0 * k,
                          I_d + q0 * k, k, W.ovf_all + q0));
   }
-  CU_TRY(cudaMemcpyAsync(W.ovf_host, W.ovf_all, sizeof(int) * nq, cudaMemcpyDeviceToHost, s));
   return B2F_OK;
 }
 
@@ -768,8 +802,8 @@ void b2f_destroy(b2f_index* idx) {
     dev_free(S.x32); dev_free(S.x16); dev_free(S.idmap); dev_free(S.maxnorm2); dev_free(S.segs_d);
     dev_free(W.cand[0]); dev_free(W.cand[1]); dev_free(W.cnt); dev_free(W.tau); dev_free(W.tauP);
     dev_free(W.ovf); dev_free(W.margin); dev_free(W.err); dev_free(W.q32); dev_free(W.q16);
-    dev_free(W.gath); dev_free(W.cnt2);
-    dev_free(W.qnorm); dev_free(W.ovf_all); dev_free(W.D); dev_free(W.I); dev_free(W.Dp); dev_free(W.Ip);
+    dev_free(W.gath); dev_free(W.cnt2); dev_free(W.hist); dev_free(W.hkey0); dev_free(W.hshift);
+    dev_free(W.qnorm); dev_free(W.D); dev_free(W.I); dev_free(W.Dp); dev_free(W.Ip);
     dev_free(W.fbq); dev_free(W.fbD); dev_free(W.fbI);
     if (W.ovf_host) cudaFreeHost(W.ovf_host);
     if (W.pin) cudaFreeHost(W.pin);

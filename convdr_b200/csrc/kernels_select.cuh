@@ -12,6 +12,7 @@ namespace b2f {
 
 constexpr int kSelThreads = 256;
 constexpr int kSortCap = 2048;  // == B2F_MAX_K
+constexpr int kTightenBuckets = 128;  // == kHistBuckets of kernels_umma.cuh
 
 struct Seg {  // rows [local_start, local_start+count) of a shard carry ids global_start + i
   int64_t local_start, count, global_start;
@@ -152,7 +153,8 @@ __global__ void __launch_bounds__(kSelThreads) refresh_kernel(
     uint64_t* __restrict__ cand_in, uint64_t* __restrict__ cand_out, uint64_t* __restrict__ gath,
     int* __restrict__ cnt, int C, int k, int exact, const float* __restrict__ margin,
     float* __restrict__ tau, uint64_t* __restrict__ tauP, int n_override, int S, int cap_p, int max_pairs,
-    int* __restrict__ cnt2, int* __restrict__ ovf) {
+    int* __restrict__ cnt2, int* __restrict__ ovf, unsigned int* __restrict__ hist /* [nq][kTightenBuckets] or null */,
+    uint32_t* __restrict__ hkey0, int* __restrict__ hshift) {
   __shared__ SelectSmem sm;
   __shared__ int seg_off[128];
   const int q = blockIdx.x;
@@ -173,12 +175,14 @@ __global__ void __launch_bounds__(kSelThreads) refresh_kernel(
   const int nvalid = block_count_valid(in, n, sm);
   uint64_t T = 0ull;
   float t = -INFINITY;
+  uint32_t kth_key = 0xffffffffu;   // key of the k-th best approximate score (approx mode)
   if (nvalid >= k) {
     const uint64_t prefix = block_kth_prefix(in, n, k, exact ? 8 : 4, sm);
     if (exact) {
       T = prefix;
       t = key2f(static_cast<uint32_t>(prefix >> 32));
     } else {
+      kth_key = static_cast<uint32_t>(prefix >> 32);
       t = __fsub_rd(key2f(static_cast<uint32_t>(prefix >> 32)), margin[q]);
       T = static_cast<uint64_t>(fkey(t)) << 32;
     }
@@ -189,6 +193,41 @@ __global__ void __launch_bounds__(kSelThreads) refresh_kernel(
     tau[q] = t;
     tauP[q] = T;
     if (m > limit) ovf[q] = 1;   // more rows within the error margin of the k-th score than the list holds
+  }
+  if (hist != nullptr) {
+    // Seed the tensor engine's tightening histogram (kernels_umma.cuh, refresher role): buckets of
+    // 2^shift score keys starting at the key of the k-th best approximate score seen so far, sized
+    // so that kTightenBuckets of them span 4x the distance from that score to the best one (a
+    // Gaussian tail moves ~1.5x that distance from 5e3 to 4e7 rows; beyond the range the last
+    // bucket absorbs everything and tightening simply stops — never a correctness matter).
+    const uint32_t key0 = kth_key;
+    int shift = 0;
+    if (key0 != 0xffffffffu) {
+      uint32_t kmax = 0;
+      for (int i = threadIdx.x; i < n; i += kSelThreads) kmax = max(kmax, static_cast<uint32_t>(in[i] >> 32));
+#pragma unroll
+      for (int s2 = 16; s2 >= 1; s2 >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, s2));
+      if (threadIdx.x == 0) sm.digit = 0;
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) atomicMax(&sm.digit, kmax);
+      __syncthreads();
+      kmax = sm.digit;
+      __syncthreads();
+      const uint64_t span = 4ull * static_cast<uint64_t>(kmax - key0) + 1ull;
+      while ((static_cast<uint64_t>(kTightenBuckets) << shift) < span) ++shift;
+    }
+    if (threadIdx.x < kTightenBuckets) sm.hist[threadIdx.x] = 0;
+    __syncthreads();
+    if (key0 != 0xffffffffu) {
+      for (int i = threadIdx.x; i < n; i += kSelThreads) {
+        const uint32_t key = static_cast<uint32_t>(in[i] >> 32);
+        if (in[i] != 0ull && key >= key0)
+          atomicAdd(&sm.hist[min(static_cast<uint32_t>(kTightenBuckets - 1), (key - key0) >> shift)], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < kTightenBuckets) hist[static_cast<int64_t>(q) * kTightenBuckets + threadIdx.x] = sm.hist[threadIdx.x];
+    if (threadIdx.x == 0) { hkey0[q] = key0; hshift[q] = shift; }
   }
 }
 
@@ -281,6 +320,187 @@ __global__ void __launch_bounds__(kSelThreads) final_kernel(
     D_out[static_cast<int64_t>(q) * out_stride + i] = s;
     I_out[static_cast<int64_t>(q) * out_stride + i] = id;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused last step of a tensor-engine (TS) pass, one 1024-thread block per query:
+//   gather (survivors of the bootstrap + every CTA pair's private area)  ->  radix-select the k-th best
+//   approximate score  ->  keep everything within the error margin of it  ->  exact fp64-accumulated
+//   rescoring (one warp per survivor, two rows in flight per warp)  ->  bitonic sort by the total
+//   order  ->  row -> id translation, (D, I) rows and the overflow flag.
+// Replaces refresh_kernel + rescore_kernel + final_kernel (three launches and two trips of the
+// lists through L2) at the end of the pass.  The lists stay in shared memory throughout
+// (2 x P records of dynamic smem; lists longer than P are gathered to `gath` in global memory).
+// ---------------------------------------------------------------------------------------------
+constexpr int kFinThreads = 512;   // two blocks per SM: 173 queries fit one wave on 148 SMs
+
+struct FinSmem {
+  unsigned int hist[256];
+  unsigned int warp_tot[kFinThreads / 32];
+  unsigned int digit, remaining, count, nvalid;
+  int seg_off[129];
+};
+
+__device__ __forceinline__ unsigned int fin_scan256(unsigned int v, FinSmem& sm) {
+  // inclusive scan of one value per thread over threads [0,256); every thread of the block calls it
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, v, s);
+    if (lane >= s) v += t;
+  }
+  if (lane == 31) sm.warp_tot[warp] = v;
+  __syncthreads();
+  unsigned int base = 0;
+  if (warp < 8)
+    for (int w = 0; w < warp; ++w) base += sm.warp_tot[w];
+  __syncthreads();
+  return v + base;
+}
+
+__global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
+    const uint64_t* __restrict__ cand, uint64_t* __restrict__ gath, const int* __restrict__ cnt, int C, int k,
+    const float* __restrict__ margin, int S, int cap_p, int max_pairs, const int* __restrict__ cnt2,
+    const int* __restrict__ ovf, int* __restrict__ ovf_out, const float* __restrict__ q32,
+    const float* __restrict__ x32, const Seg* __restrict__ segs, int nseg, const int64_t* __restrict__ idmap,
+    float* __restrict__ D_out, int64_t* __restrict__ I_out, int64_t out_stride, int P) {
+  extern __shared__ __align__(16) uint64_t fin_buf[];   // [2][P]
+  __shared__ FinSmem sm;
+  __shared__ __align__(16) float Qs[kD];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t* list = cand + static_cast<int64_t>(q) * C;
+  uint64_t* bufA = fin_buf;
+  uint64_t* bufB = fin_buf + P;
+  for (int i = tid; i < kD; i += kFinThreads) Qs[i] = q32[static_cast<int64_t>(q) * kD + i];
+
+  // ---- 1. segment offsets ----
+  const int m = min(cnt[q], S);
+  {
+    unsigned int c = 0;
+    if (tid < max_pairs) c = static_cast<unsigned int>(min(cnt2[q * max_pairs + tid], cap_p));
+    const unsigned int inc = fin_scan256(tid < 256 ? c : 0u, sm);
+    if (tid < max_pairs) sm.seg_off[tid] = static_cast<int>(inc - c);
+    if (tid == max_pairs - 1) sm.seg_off[max_pairs] = static_cast<int>(inc);
+    __syncthreads();
+  }
+  const int n = m + sm.seg_off[max_pairs];
+  uint64_t* in = (n <= P) ? bufA : gath + static_cast<int64_t>(q) * C;
+
+  // ---- 2. gather ----
+  for (int i = tid; i < m; i += kFinThreads) in[i] = list[i];
+  for (int p = warp; p < max_pairs; p += kFinThreads / 32) {
+    const int off = sm.seg_off[p], c = sm.seg_off[p + 1] - off;
+    const uint64_t* src = list + S + static_cast<int64_t>(p) * cap_p;
+    for (int e = lane; e < c; e += 32) in[m + off + e] = src[e];
+  }
+  if (tid == 0) { sm.nvalid = 0; sm.count = 0; }
+  __syncthreads();
+
+  // ---- 3. k-th best approximate score (radix select on the 32-bit score key) ----
+  {
+    unsigned int c = 0;
+    for (int i = tid; i < n; i += kFinThreads) c += (in[i] != 0ull);
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+    if (lane == 0 && c) atomicAdd(&sm.nvalid, c);
+    __syncthreads();
+  }
+  const int nvalid = static_cast<int>(sm.nvalid);
+  uint64_t T = 0ull;
+  if (nvalid >= k) {
+    uint32_t prefix = 0, mask = 0;
+    unsigned int remaining = static_cast<unsigned int>(k);
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      if (tid < 256) sm.hist[tid] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += kFinThreads) {
+        const uint32_t key = static_cast<uint32_t>(in[i] >> 32);
+        if (key != 0u && (key & mask) == prefix) atomicAdd(&sm.hist[(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      const unsigned int h = (tid < 256) ? sm.hist[255 - tid] : 0u;   // thread t owns bucket 255-t (descending)
+      const unsigned int cum = fin_scan256(h, sm);
+      if (tid < 256 && cum >= remaining && cum - h < remaining) {
+        sm.digit = 255u - tid;
+        sm.remaining = remaining - (cum - h);
+      }
+      __syncthreads();
+      prefix |= sm.digit << shift;
+      mask |= 0xffu << shift;
+      remaining = sm.remaining;
+      __syncthreads();
+    }
+    const float t = __fsub_rd(key2f(prefix), margin[q]);
+    T = static_cast<uint64_t>(fkey(t)) << 32;
+  }
+
+  // ---- 4. survivors: every record within the margin of the k-th score ----
+  for (int i0 = 0; i0 < n; i0 += kFinThreads) {
+    const int i = i0 + tid;
+    const uint64_t rec = (i < n) ? in[i] : 0ull;
+    const bool keep = rec != 0ull && rec >= T;
+    const unsigned int b = __ballot_sync(0xffffffffu, keep);
+    if (b) {
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(&sm.count, __popc(b));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const unsigned int pos = base + __popc(b & ((1u << lane) - 1u));
+      if (keep && pos < static_cast<unsigned int>(S)) bufB[pos] = rec;
+    }
+  }
+  __syncthreads();
+  const int m2_all = static_cast<int>(sm.count);
+  const int m2 = min(m2_all, S);
+
+  // ---- 5. exact rescoring, in place ----
+  const float4* q4 = reinterpret_cast<const float4*>(Qs);
+  for (int c = warp; c < m2; c += 2 * (kFinThreads / 32)) {
+    const int c2 = c + kFinThreads / 32;
+    const uint32_t rowA = cand_row(bufB[c]);
+    const uint32_t rowB = (c2 < m2) ? cand_row(bufB[c2]) : rowA;
+    const double a = lane_partial_f64(q4, reinterpret_cast<const float4*>(x32 + static_cast<int64_t>(rowA) * kD), lane);
+    const double b = lane_partial_f64(q4, reinterpret_cast<const float4*>(x32 + static_cast<int64_t>(rowB) * kD), lane);
+    const float sa = static_cast<float>(warp_butterfly_sum(a));
+    const float sb = static_cast<float>(warp_butterfly_sum(b));
+    if (lane == 0) {
+      bufB[c] = pack_cand(sa, rowA);
+      if (c2 < m2) bufB[c2] = pack_cand(sb, rowB);
+    }
+  }
+  int P2 = 32;
+  while (P2 < m2) P2 <<= 1;
+  for (int i = m2 + tid; i < P2; i += kFinThreads) bufB[i] = 0ull;
+  __syncthreads();
+
+  // ---- 6. bitonic sort, descending by (score, row asc) ----
+  for (int size = 2; size <= P2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (P2 >> 1); i += kFinThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t a = bufB[lo], b = bufB[hi];
+        if ((a < b) == desc) { bufB[lo] = b; bufB[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- 7. output ----
+  for (int i = tid; i < k; i += kFinThreads) {
+    const uint64_t rec = (i < P2) ? bufB[i] : 0ull;
+    float s = -3.402823466e+38f;
+    int64_t id = -1;
+    if (rec != 0ull) {
+      s = cand_score(rec);
+      id = row_to_id(cand_row(rec), segs, nseg, idmap);
+    }
+    D_out[static_cast<int64_t>(q) * out_stride + i] = s;
+    I_out[static_cast<int64_t>(q) * out_stride + i] = id;
+  }
+  if (tid == 0 && ovf_out) ovf_out[q] = (ovf[q] != 0 || m2_all > S) ? 1 : 0;
 }
 
 // Cross-shard merge: parts [G][nq][k] (each sorted by score desc, padded with id = -1) -> [nq][k].

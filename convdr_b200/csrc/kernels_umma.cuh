@@ -39,7 +39,8 @@ constexpr int kTmemCols = 512;
 constexpr int kTmemColsA = kD / 2;             // 384 columns: 128 lanes x 768 bf16
 constexpr int kTmemColD = kTmemColsA;          // accumulators: columns [384, 512)
 constexpr int kAccStages = (kTmemCols - kTmemColsA) / kTileRows;    // 2 (double-buffered)
-constexpr int kUmmaTailBytes = 2048;           // barriers, tmem pointer, refresher histogram
+constexpr int kUmmaTailBytes = 2048;           // barriers, tmem pointer
+constexpr int kHistBuckets = 128;              // tightening histogram: one uint4 per refresher lane
 constexpr int kUmmaSmemBytes = kNumStages * kStageBytes + kUmmaTailBytes + 1024;  // + alignment slack
 static_assert(kUmmaSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
 static_assert(kAccStages >= 1 && kAccStages <= 2, "TMEM budget: 384 query columns + accumulators in 128 columns");
@@ -60,12 +61,17 @@ struct UmmaArgs {
   float* tau;                 // [nq] thresholds (raised in-kernel when tighten != 0)
   int* ovf;                   // [nq] set when a private area was too small
   int* err;                   // device error flag (barrier timeout)
-  // in-kernel threshold tightening (see the refresher role below)
-  int tighten;                // >0: the idle warp of each CTA keeps re-selecting tau while the stream runs;
-                              //     the value is the pause between rounds in ns
+  // In-kernel threshold tightening (see the refresher role below).  Every hit is also counted in a
+  // per-query histogram over the score-key range above the bootstrap's k-th score:
+  //   bucket(key) = min(kHistBuckets-1, (key - hkey0[q]) >> hshift[q])   for key >= hkey0[q]
+  // so "k rows seen so far score at least edge(b)" is one suffix sum away.
+  int tighten;                // >0: the idle warp of each CTA keeps raising tau[q] while the stream runs;
+                              //     the value is the pause between its rounds in ns
   int k;
   const float* margin;        // [nq] 2*eps of the prefilter
-  const int* surv_cnt;        // [nq] valid survivors in [0, S)
+  unsigned int* hist;         // [nq][kHistBuckets], initialised by refresh_kernel after the bootstrap
+  const uint32_t* hkey0;      // [nq] key of the bootstrap's k-th best approximate score (0xffffffff: none yet)
+  const int* hshift;          // [nq] log2(keys per bucket)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -257,7 +263,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
   const uint32_t bar_tempty = bar_tfull + 16;                     // [2]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(base_ptr + kNumStages * kStageBytes + 16 * kNumStages + 40);
   volatile int* epi_done_s = reinterpret_cast<volatile int*>(tmem_ptr_s + 1);     // epilogue warps that finished
-  unsigned int* hist_s = reinterpret_cast<unsigned int*>(base_ptr + kNumStages * kStageBytes + 512);  // [256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -348,15 +353,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     const bool q_ok = q < a.nq;
     {
       const uint4* src = reinterpret_cast<const uint4*>(a.q16 + static_cast<int64_t>(q_ok ? q : 0) * kD);
+      // three 128-byte chunks (3 x 8 independent 16-byte loads) in flight per round: 4 L2 round trips
+      // for the whole 1536-byte query row instead of 12
+      constexpr int kQChunk = 3;
+      static_assert((kTmemColsA / 32) % kQChunk == 0, "query row = whole rounds");
 #pragma unroll 1
-      for (int c = 0; c < kTmemColsA / 32; ++c) {   // 32 columns = 64 bf16 = 128 bytes per step
-        uint32_t w[32];
+      for (int c0 = 0; c0 < kTmemColsA / 32; c0 += kQChunk) {   // 32 columns = 64 bf16 = 128 bytes per chunk
+        uint32_t w[kQChunk][32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint4 t = q_ok ? __ldg(src + c * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
-          w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
-        }
-        tmem_st_x32(lane_addr + 32 * c, w);
+        for (int u = 0; u < kQChunk; ++u)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint4 t = q_ok ? __ldg(src + (c0 + u) * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
+            w[u][4 * i] = t.x; w[u][4 * i + 1] = t.y; w[u][4 * i + 2] = t.z; w[u][4 * i + 3] = t.w;
+          }
+#pragma unroll
+        for (int u = 0; u < kQChunk; ++u) tmem_st_x32(lane_addr + 32 * (c0 + u), w[u]);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -365,11 +377,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     }
     float tau = (q_ok && !a.dense) ? a.tau[q] : INFINITY;
     volatile float* tau_g = a.tau + (q_ok ? q : 0);
-    volatile int* my_cnt = a.cnt2 + (q_ok ? q : 0) * a.max_pairs + pair;
+    int* my_cnt = a.cnt2 + (q_ok ? q : 0) * a.max_pairs + pair;
     const bool live = a.tighten && q_ok && !a.dense;
-    int n_pub = 0;    // entries already published to the refresher
+    const uint32_t hkey0 = live ? a.hkey0[q] : 0xffffffffu;
+    const int hshift = live ? a.hshift[q] : 0;
+    unsigned int* my_hist = a.hist + static_cast<int64_t>(q_ok ? q : 0) * kHistBuckets;
     uint64_t* my_list = a.cand + static_cast<int64_t>(q_ok ? q : 0) * a.C + a.S + static_cast<int64_t>(pair) * a.cap_p;
     int n_mine = 0;   // entries this thread appended for (query q, this pair)
+    // count a hit in the tightening histogram (fire-and-forget RED; hits are rare)
+    auto count_hit = [&](uint32_t bits) {
+      const uint32_t key = fkey(__uint_as_float(bits));
+      if (key >= hkey0) atomicAdd(my_hist + min(static_cast<uint32_t>(kHistBuckets - 1), (key - hkey0) >> hshift), 1u);
+    };
     const uint32_t tempty_leader = mapa_u32(bar_tempty, 0);
     int it = 0;
     for (int tile = a.tile_begin + pair; tile < a.tile_end; tile += npairs, ++it) {
@@ -420,6 +439,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
                   const int slot = n_mine + __popc(m & ((1u << c) - 1u));
                   if (slot < a.cap_p)
                     my_list[slot] = pack_cand(__uint_as_float(v[32 * w + c]), static_cast<uint32_t>(row0 + 32 * w + c));
+                  count_hit(v[32 * w + c]);
                 }
               }
               n_mine += __popc(m);
@@ -433,6 +453,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
               if ((m >> c) & 1u) {   // no atomics: the area is private to this thread
                 if (n_mine < a.cap_p) my_list[n_mine] = pack_cand(__uint_as_float(bits), static_cast<uint32_t>(row0 + 32 * w + c));
                 ++n_mine;
+                count_hit(bits);
               }
             }
           }
@@ -441,13 +462,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * as);   // this accumulator stage is free again
-      if (live && n_mine != n_pub) {
-        // Publish the new entries to the refresher.  No fence (a MEMBAR.GPU per tile would dominate):
-        // private areas are all-zero before the launch and a record is one 8-byte store, so a slot
-        // the refresher reads ahead of its store is 0 and is skipped.
-        *my_cnt = min(n_mine, a.cap_p);
-        n_pub = n_mine;
-      }
     }
     if (q_ok) {
       *my_cnt = min(n_mine, a.cap_p);
@@ -457,110 +471,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     if (lane == 0) atomicAdd(const_cast<int*>(epi_done_s), 1);
   } else if (warp == 3 && a.tighten && !a.dense) {
     // ===================== refresher: in-kernel threshold tightening =====================
-    // While the stream runs, this otherwise idle warp keeps recomputing, for the queries assigned
-    // to this CTA, the k-th best approximate score among everything published so far (survivors of
-    // the bootstrap + every pair's private area) and raises tau[q] = kth - 2*eps.  Any subset of the
-    // rows seen gives a valid (lower) bound, so no synchronisation with the writers is needed: slots
-    // not yet written read as 0 (the areas are zero before the launch) and are skipped.  Effect: the pass rate follows k/rows_seen
-    // continuously instead of per launch, so one launch covers the whole shard.
-    const int nseg = a.max_pairs;
-    int last_total[4] = {-1, -1, -1, -1};
+    // While the stream runs, this otherwise idle warp keeps reading, for the queries assigned to
+    // this CTA (q = blockIdx.x, + gridDim.x, ...), the histogram of hits above the bootstrap's k-th
+    // score and raises tau[q] to (lower edge of the highest bucket b with >= k hits in buckets >= b)
+    // - 2*eps.  At least k rows seen so far have an approximate score >= that edge, so the k-th best
+    // approximate score of any superset is >= it: the bound of DESIGN.md section 4 holds for every
+    // intermediate value, whatever the interleaving (counts only grow; a stale read is a smaller
+    // suffix sum, i.e. a lower, still valid, threshold).  Every hit with key >= hkey0 is counted by
+    // every pair because all thresholds in use are <= the current one.  Effect: the pass rate
+    // follows k/rows_seen continuously, so ONE launch streams the whole shard after the bootstrap.
+    float last[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     while (*epi_done_s < 4) {
       int qi = 0;
       for (int q = blockIdx.x; q < a.nq; q += gridDim.x, ++qi) {
-        const uint64_t* list = a.cand + static_cast<int64_t>(q) * a.C;
-        const volatile int* cnts = a.cnt2 + q * a.max_pairs;
-        const int m = min(a.surv_cnt[q], a.S);
-        // segment lengths owned by this lane (segment s = lane, lane+32, ...; s == nseg: survivors)
-        int total = 0;
-        int len[4];
+        const uint32_t key0 = a.hkey0[q];
+        if (key0 == 0xffffffffu) continue;     // fewer than k rows seen by the bootstrap: nothing to reject
+        const uint4 h = __ldcv(reinterpret_cast<const uint4*>(a.hist + static_cast<int64_t>(q) * kHistBuckets) + lane);
+        const unsigned int mine = h.x + h.y + h.z + h.w;
+        unsigned int suf = mine;               // hits in the buckets of lanes >= this one
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int sgm = lane + 32 * j;
-          len[j] = (sgm < nseg) ? cnts[sgm] : 0;
-          total += len[j];
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int t = __shfl_down_sync(0xffffffffu, suf, o);
+          if (lane + o < 32) suf += t;
         }
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-        total += m;
-        if (total < a.k || (qi < 4 && total == last_total[qi])) continue;   // nothing new since last time
-        if (qi < 4) last_total[qi] = total;
-        uint32_t prefix = 0, mask = 0;
-        unsigned int remaining = static_cast<unsigned int>(a.k);
-        for (int pass = 0; pass < 4; ++pass) {   // radix select on the 32-bit score key
-          const int shift = 24 - 8 * pass;
-#pragma unroll
-          for (int b = 0; b < 8; ++b) hist_s[lane + 32 * b] = 0;
-          __syncwarp();
-          // survivors of the bootstrap: 4 independent loads per lane and round
-          for (int i0 = 0; i0 < m; i0 += 128) {
-            uint32_t key[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = i0 + 32 * u + lane;
-              key[u] = (i < m) ? static_cast<uint32_t>(__ldcg(list + i) >> 32) : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (key[u] != 0u && (key[u] & mask) == prefix) atomicAdd(&hist_s[(key[u] >> shift) & 255u], 1u);
-          }
-          // private areas: 8 segments per round, lane e reads entry e of each (loads are independent,
-          // so one L2 latency covers the round instead of one per entry)
-          for (int s0 = 0; s0 < nseg; s0 += 8) {
-            int L[8], maxlen = 0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int sg = s0 + u, j = sg >> 5;
-              const int mine = (j == 0) ? len[0] : (j == 1) ? len[1] : (j == 2) ? len[2] : len[3];
-              L[u] = __shfl_sync(0xffffffffu, mine, sg & 31);
-              if (sg >= nseg) L[u] = 0;
-              maxlen = max(maxlen, L[u]);
-            }
-            for (int e0 = 0; e0 < maxlen; e0 += 32) {
-              uint32_t key[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int e = e0 + lane;
-                key[u] = (e < L[u]) ? static_cast<uint32_t>(__ldcg(list + a.S + static_cast<int64_t>(s0 + u) * a.cap_p + e) >> 32) : 0u;
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u)
-                if (key[u] != 0u && (key[u] & mask) == prefix) atomicAdd(&hist_s[(key[u] >> shift) & 255u], 1u);
-            }
-          }
-          __syncwarp();
-          // lane l owns buckets 255-8l .. 248-8l (descending); find the bucket holding the `remaining`-th
-          unsigned int h[8], sum = 0;
-#pragma unroll
-          for (int b = 0; b < 8; ++b) { h[b] = hist_s[255 - (8 * lane + b)]; sum += h[b]; }
-          unsigned int inc = sum;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-          }
-          unsigned int before = inc - sum;   // keys in higher buckets owned by lower lanes
-          int digit = -1;
-          unsigned int rem_new = 0;
-          if (inc >= remaining && before < remaining) {
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-              if (digit < 0 && before + h[b] >= remaining) { digit = 255 - (8 * lane + b); rem_new = remaining - before; }
-              before += h[b];
-            }
-          }
-          const unsigned int who = __ballot_sync(0xffffffffu, digit >= 0);
-          if (who == 0u) { prefix = 0; break; }   // cannot happen (total >= k); never publish a bogus bound
-          const int src = __ffs(who) - 1;
-          digit = __shfl_sync(0xffffffffu, digit, src);
-          remaining = __shfl_sync(0xffffffffu, rem_new, src);
-          prefix |= static_cast<uint32_t>(digit) << shift;
-          mask |= 0xffu << shift;
-          __syncwarp();
+        const unsigned int kk = static_cast<unsigned int>(a.k);
+        unsigned int above = suf - mine;
+        int b = -1;
+        if (suf >= kk && above < kk) {         // exactly one lane
+          above += h.w; b = 4 * lane + 3;
+          if (above < kk) { above += h.z; b = 4 * lane + 2; }
+          if (above < kk) { above += h.y; b = 4 * lane + 1; }
+          if (above < kk) { b = 4 * lane; }
         }
-        if (lane == 0 && prefix != 0u) {
-          const float t = __fsub_rd(key2f(prefix), a.margin[q]);
-          if (t > a.tau[q]) *reinterpret_cast<volatile float*>(a.tau + q) = t;
+        const unsigned int who = __ballot_sync(0xffffffffu, b >= 0);
+        if (who == 0u) continue;
+        b = __shfl_sync(0xffffffffu, b, __ffs(who) - 1);
+        if (lane == 0) {
+          const uint64_t edge = static_cast<uint64_t>(key0) + (static_cast<uint64_t>(b) << a.hshift[q]);
+          if (edge <= 0xff7fffffull) {         // a finite score key
+            const float t = __fsub_rd(key2f(static_cast<uint32_t>(edge)), a.margin[q]);
+            const float prev = (qi < 4) ? last[qi] : *reinterpret_cast<volatile float*>(a.tau + q);
+            if (t > prev) {
+              *reinterpret_cast<volatile float*>(a.tau + q) = t;
+              if (qi < 4) last[qi] = t;
+            }
+          }
         }
       }
       __nanosleep(static_cast<unsigned int>(a.tighten));

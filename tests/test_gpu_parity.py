@@ -309,9 +309,9 @@ def test_device_resident_search_and_merge_kernel():
 
 def test_in_kernel_threshold_tightening_gives_identical_results(c1_data):
     P, Q = c1_data
-    base = make_index("umma_ts", P)
+    base = make_index("umma_ts", P, tighten=0, growth=4)   # geometric phases, refresh kernel between them
     D0, I0 = base.search(Q, 100)
-    tight = make_index("umma_ts", P, tighten=2000)
+    tight = make_index("umma_ts", P)                # default: histogram tightening inside one launch
     D1, I1 = tight.search(Q, 100)
     np.testing.assert_array_equal(I1, I0)
     np.testing.assert_array_equal(D1, D0)
