@@ -91,6 +91,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint32_t c
   return B2F_OK;
 }
 
+constexpr int kMaxPending = 16;   // asynchronous device searches in flight (one overflow-flag slot each)
+
 struct Workspace {
   // candidate state of one pass
   int qp_cap = 0, C = 0;
@@ -174,9 +176,16 @@ struct Shard {
 
 }  // namespace
 
+struct Pending {
+  const float* q; int64_t nq; int k; float* D; int64_t* I; int slot;
+};
+
 struct b2f_index {
   int d = kD;
   std::vector<Shard> shards;
+  std::vector<Pending> pending;   // enqueued by b2f_search_device_async, settled by b2f_search_finish
+  int* merge_flag_host = nullptr; // mapped host int: a packed merge saw a part whose list had overflowed
+  int* merge_flag_dev = nullptr;
   int64_t ntotal = 0;
   // options
   int path = B2F_PATH_AUTO;
@@ -292,7 +301,8 @@ int ensure_query_ws(Shard& S, int64_t nq, int k) {
     B2F_TRY(dev_alloc(&W.qnorm, static_cast<size_t>(cap + kUmmaMaxQ + 16)));
     // per-query overflow flags live in mapped pinned host memory: the last kernel of a pass writes them
     // straight to the host (no copy operation on the stream), the host reads them after the sync
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&W.ovf_host), static_cast<size_t>(cap) * sizeof(int), cudaHostAllocMapped));
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&W.ovf_host), static_cast<size_t>(cap) * kMaxPending * sizeof(int),
+                         cudaHostAllocMapped));
     CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&W.ovf_all), W.ovf_host, 0));
     W.nq_cap = cap;
   }
@@ -609,7 +619,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     }
     final_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.cnt, C, k, S.segs_d,
                                             static_cast<int>(S.segs.size()), S.has_ids ? S.idmap : nullptr,
-                                            D_out, I_out, out_stride);
+                                            D_out, I_out, out_stride, W.ovf);
   }
   CU_TRY(cudaGetLastError());
   st.launches += 1;
@@ -629,14 +639,17 @@ int resolve_path(const b2f_index* idx, const Shard& S, int64_t nq) {
 }
 
 // Enqueue the whole search of one shard.  q_d: fp32 queries on the shard's device.
-int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d) {
+int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d,
+                   int slot = 0) {
   CU_TRY(cudaSetDevice(S.dev));
   Workspace& W = S.ws;
   cudaStream_t s = S.stream;
+  int* ovf_slot_host = W.ovf_host + static_cast<size_t>(slot) * W.nq_cap;
+  int* ovf_slot = W.ovf_all + static_cast<size_t>(slot) * W.nq_cap;
   if (S.n == 0) {
     fill_pad_kernel<<<static_cast<int>((nq * k + 255) / 256), 256, 0, s>>>(D_d, I_d, nq * k);
     CU_TRY(cudaGetLastError());
-    std::memset(W.ovf_host, 0, sizeof(int) * nq);   // no kernel writes the flags of an empty shard
+    std::memset(ovf_slot_host, 0, sizeof(int) * nq);   // no kernel writes the flags of an empty shard
     return B2F_OK;
   }
   const int path = resolve_path(idx, S, nq);
@@ -668,23 +681,27 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
   for (int64_t q0 = 0; q0 < nq; q0 += plan.qp) {
     const int nqp = static_cast<int>(std::min<int64_t>(plan.qp, nq - q0));
     B2F_TRY(enqueue_pass(idx, S, plan, q_d + q0 * kD, W.q16 + q0 * kD, W.qnorm + q0, nqp, k, D_d + q0 * k,
-                         I_d + q0 * k, k, W.ovf_all + q0));
+                         I_d + q0 * k, k, ovf_slot + q0));
   }
   return B2F_OK;
 }
 
 // After the stream drained: re-run any query whose candidate list overflowed on the exact engine
 // (bounded phases, cannot overflow).  Normally a no-op.
-int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d) {
+int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d,
+                  int slot = 0, bool* reran = nullptr) {
   CU_TRY(cudaSetDevice(S.dev));
   CU_TRY(cudaStreamSynchronize(S.stream));
   if (idx->profile) collect_prof(idx, S);
+  if (reran) *reran = false;
   if (S.n == 0) return B2F_OK;
   Workspace& W = S.ws;
+  const int* flags = W.ovf_host + static_cast<size_t>(slot) * W.nq_cap;
   std::vector<int64_t> bad;
   for (int64_t q = 0; q < nq; ++q)
-    if (W.ovf_host[q]) bad.push_back(q);
+    if (flags[q]) bad.push_back(q);
   if (bad.empty()) return B2F_OK;
+  if (reran) *reran = true;
   idx->stats.fallback_queries += static_cast<double>(bad.size());
   static bool attr_set3[64] = {false};
   if (!attr_set3[S.dev & 63]) {
@@ -710,6 +727,26 @@ int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k,
   CU_TRY(cudaStreamSynchronize(s));
   if (idx->profile) collect_prof(idx, S);
   return B2F_OK;
+}
+
+// Settle every search enqueued by b2f_search_device_async: wait for the stream, then re-run (on the
+// exact engine) the queries whose candidate lists overflowed.  Normally just the synchronisation.
+int settle_pending(b2f_index* idx) {
+  if (idx->pending.empty()) return B2F_OK;
+  Shard& S = idx->shards[0];
+  std::vector<Pending> todo;
+  todo.swap(idx->pending);
+  for (const Pending& p : todo) B2F_TRY(finish_search(idx, S, p.q, p.nq, p.k, p.D, p.I, p.slot));
+  return B2F_OK;
+}
+
+// True when enqueueing this search would (re)allocate a workspace that searches in flight still use.
+bool search_would_realloc(const b2f_index* idx, const Shard& S, int64_t nq, int k) {
+  const Workspace& W = S.ws;
+  if (nq > W.nq_cap || nq * k > W.out_cap || !W.fbq) return true;
+  if (S.n == 0) return false;
+  const PassPlan plan = make_plan(idx, S, resolve_path(idx, S, nq), k, nq);
+  return plan.qp > W.qp_cap || plan.C > W.C;
 }
 
 int check_args_search(const b2f_index* idx, const void* q, int64_t nq, int k, const void* D, const void* I) {
@@ -778,6 +815,16 @@ int b2f_create(int d, const int* devices, int n_dev, b2f_index** out) {
     S.sm_count = prop.multiProcessorCount;
     S.max_pairs = std::min(128, std::max(1, S.sm_count / 2));
   }
+  {
+    cudaSetDevice(idx->shards[0].dev);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&idx->merge_flag_host), sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&idx->merge_flag_dev), idx->merge_flag_host, 0) != cudaSuccess) {
+      (void)cudaGetLastError();
+      b2f_destroy(idx);
+      return fail(B2F_ERR_CUDA, "mapped host allocation failed");
+    }
+    *idx->merge_flag_host = 0;
+  }
   // peer access between shard devices (direct NVLink copies for the result gather)
   for (size_t i = 0; i < devs.size(); ++i)
     for (size_t j = 0; j < devs.size(); ++j) {
@@ -795,6 +842,7 @@ int b2f_create(int d, const int* devices, int n_dev, b2f_index** out) {
 
 void b2f_destroy(b2f_index* idx) {
   if (!idx) return;
+  idx->pending.clear();
   for (Shard& S : idx->shards) {
     cudaSetDevice(S.dev);
     if (S.stream) cudaStreamSynchronize(S.stream);
@@ -811,6 +859,7 @@ void b2f_destroy(b2f_index* idx) {
     if (S.ev) cudaEventDestroy(S.ev);
     if (S.stream) cudaStreamDestroy(S.stream);
   }
+  if (idx->merge_flag_host) cudaFreeHost(idx->merge_flag_host);
   (void)cudaGetLastError();
   delete idx;
 }
@@ -829,6 +878,7 @@ void* b2f_stream(b2f_index* idx, int shard) {
 int b2f_reserve(b2f_index* idx, int64_t n_per_shard) {
   if (!idx || n_per_shard < 0) return fail(B2F_ERR_INVALID, "bad reserve arguments");
   if (n_per_shard >= 0xfffffff0ll) return fail(B2F_ERR_INVALID, "a shard holds at most 2^32-16 rows");
+  B2F_TRY(settle_pending(idx));
   for (Shard& S : idx->shards) B2F_TRY(ensure_capacity(idx, S, n_per_shard));
   return B2F_OK;
 }
@@ -837,6 +887,7 @@ static int add_impl(b2f_index* idx, const float* x_host, const int64_t* ids_host
   if (!idx) return fail(B2F_ERR_INVALID, "null index");
   if (n < 0 || (n > 0 && !x_host)) return fail(B2F_ERR_INVALID, "bad add arguments");
   if (n == 0) return B2F_OK;
+  B2F_TRY(settle_pending(idx));
   const int G = static_cast<int>(idx->shards.size());
   if (ids_host) {
     for (Shard& S : idx->shards)
@@ -884,6 +935,7 @@ int b2f_add_device(b2f_index* idx, int shard, const float* x_dev, int64_t n) {
   if (!idx || shard < 0 || shard >= static_cast<int>(idx->shards.size()) || n < 0 || (n > 0 && !x_dev))
     return fail(B2F_ERR_INVALID, "bad add_device arguments");
   if (n == 0) return B2F_OK;
+  B2F_TRY(settle_pending(idx));
   Shard& S = idx->shards[shard];
   if (S.has_ids && S.n > 0) return fail(B2F_ERR_INVALID, "index uses explicit ids");
   CU_TRY(cudaSetDevice(S.dev));
@@ -902,6 +954,7 @@ int b2f_add_synthetic(b2f_index* idx, int shard, int64_t first_row, int64_t n, u
   if (!idx || shard < 0 || shard >= static_cast<int>(idx->shards.size()) || n < 0 || first_row < 0)
     return fail(B2F_ERR_INVALID, "bad add_synthetic arguments");
   if (n == 0) return B2F_OK;
+  B2F_TRY(settle_pending(idx));
   Shard& S = idx->shards[shard];
   if (S.has_ids && S.n > 0) return fail(B2F_ERR_INVALID, "index uses explicit ids");
   CU_TRY(cudaSetDevice(S.dev));
@@ -932,6 +985,7 @@ int b2f_reconstruct_n(b2f_index* idx, int shard, int64_t row0, int64_t n, float*
 
 int b2f_reset(b2f_index* idx) {
   if (!idx) return fail(B2F_ERR_INVALID, "null index");
+  B2F_TRY(settle_pending(idx));
   for (Shard& S : idx->shards) {
     CU_TRY(cudaSetDevice(S.dev));
     CU_TRY(cudaStreamSynchronize(S.stream));
@@ -952,6 +1006,7 @@ int b2f_search_device(b2f_index* idx, const float* q_dev, int64_t nq, int k, flo
   B2F_TRY(check_args_search(idx, q_dev, nq, k, D_dev, I_dev));
   if (idx->shards.size() != 1) return fail(B2F_ERR_INVALID, "b2f_search_device needs a single-shard index");
   if (nq == 0) return B2F_OK;
+  B2F_TRY(settle_pending(idx));
   reset_stats(idx);
   Shard& S = idx->shards[0];
   CU_TRY(cudaSetDevice(S.dev));
@@ -961,6 +1016,26 @@ int b2f_search_device(b2f_index* idx, const float* q_dev, int64_t nq, int k, flo
   return B2F_OK;
 }
 
+int b2f_search_device_async(b2f_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+  B2F_TRY(check_args_search(idx, q_dev, nq, k, D_dev, I_dev));
+  if (idx->shards.size() != 1) return fail(B2F_ERR_INVALID, "b2f_search_device_async needs a single-shard index");
+  if (nq == 0) return B2F_OK;
+  Shard& S = idx->shards[0];
+  CU_TRY(cudaSetDevice(S.dev));
+  if (static_cast<int>(idx->pending.size()) >= kMaxPending || search_would_realloc(idx, S, nq, k))
+    B2F_TRY(settle_pending(idx));
+  B2F_TRY(ensure_query_ws(S, nq, k));
+  const int slot = static_cast<int>(idx->pending.size());
+  B2F_TRY(enqueue_search(idx, S, q_dev, nq, k, D_dev, I_dev, slot));
+  idx->pending.push_back(Pending{q_dev, nq, k, D_dev, I_dev, slot});
+  return B2F_OK;
+}
+
+int b2f_search_finish(b2f_index* idx) {
+  if (!idx) return fail(B2F_ERR_INVALID, "null index");
+  return settle_pending(idx);
+}
+
 int b2f_merge_device(b2f_index* idx, const float* D_parts_dev, const int64_t* I_parts_dev, int n_parts,
                      int64_t nq, int k, float* D_dev, int64_t* I_dev) {
   if (!idx || n_parts < 1 || nq < 0 || k < 1 || !D_parts_dev || !I_parts_dev || !D_dev || !I_dev)
@@ -968,16 +1043,35 @@ int b2f_merge_device(b2f_index* idx, const float* D_parts_dev, const int64_t* I_
   if (nq == 0) return B2F_OK;
   Shard& S = idx->shards[0];
   CU_TRY(cudaSetDevice(S.dev));
-  merge_kernel<<<static_cast<int>(nq), 256, 0, S.stream>>>(D_parts_dev, I_parts_dev, n_parts, nq, k, D_dev, I_dev);
+  merge_kernel<<<static_cast<int>(nq), 256, 0, S.stream>>>(D_parts_dev, I_parts_dev, n_parts, nq, k, D_dev, I_dev,
+                                                           nq * k, nq * k, nullptr);
   CU_TRY(cudaGetLastError());
   idx->stats.launches += 1;
   CU_TRY(cudaStreamSynchronize(S.stream));
   return B2F_OK;
 }
 
+int b2f_merge_packed_device_async(b2f_index* idx, const void* parts_dev, int n_parts, int64_t part_bytes,
+                                  int64_t i_offset_bytes, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+  if (!idx || n_parts < 1 || nq < 0 || k < 1 || !parts_dev || !D_dev || !I_dev || part_bytes % 8 != 0 ||
+      i_offset_bytes % 8 != 0 || i_offset_bytes < nq * k * 4 || part_bytes < i_offset_bytes + nq * k * 8)
+    return fail(B2F_ERR_INVALID, "bad packed merge arguments");
+  if (nq == 0) return B2F_OK;
+  Shard& S = idx->shards[0];
+  CU_TRY(cudaSetDevice(S.dev));
+  const char* base = static_cast<const char*>(parts_dev);
+  merge_kernel<<<static_cast<int>(nq), 256, 0, S.stream>>>(
+      reinterpret_cast<const float*>(base), reinterpret_cast<const int64_t*>(base + i_offset_bytes), n_parts, nq, k,
+      D_dev, I_dev, part_bytes / 4, part_bytes / 8, idx->merge_flag_dev);
+  CU_TRY(cudaGetLastError());
+  idx->stats.launches += 1;
+  return B2F_OK;
+}
+
 int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_host, int64_t* I_host) {
   B2F_TRY(check_args_search(idx, q_host, nq, k, D_host, I_host));
   if (nq == 0) return B2F_OK;
+  B2F_TRY(settle_pending(idx));
   reset_stats(idx);
   const int G = static_cast<int>(idx->shards.size());
   const size_t qbytes = static_cast<size_t>(nq) * kD * 4;
@@ -994,6 +1088,24 @@ int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_
     B2F_TRY(ensure_query_ws(S, nq, k));
     CU_TRY(cudaMemcpyAsync(S.ws.q32, S0.ws.pin, qbytes, cudaMemcpyHostToDevice, S.stream));
     B2F_TRY(enqueue_search(idx, S, S.ws.q32, nq, k, S.ws.D, S.ws.I));
+  }
+  float* pinD = reinterpret_cast<float*>(S0.ws.pin);
+  int64_t* pinI = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(S0.ws.pin) + d_off);
+  if (G == 1) {
+    // single shard: the download is enqueued behind the search, ONE synchronisation; only if a
+    // candidate list overflowed (rare) the affected queries are re-run and downloaded again
+    CU_TRY(cudaMemcpyAsync(pinD, S0.ws.D, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
+    CU_TRY(cudaMemcpyAsync(pinI, S0.ws.I, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
+    bool reran = false;
+    B2F_TRY(finish_search(idx, S0, S0.ws.q32, nq, k, S0.ws.D, S0.ws.I, 0, &reran));
+    if (reran) {
+      CU_TRY(cudaMemcpyAsync(pinD, S0.ws.D, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
+      CU_TRY(cudaMemcpyAsync(pinI, S0.ws.I, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
+      CU_TRY(cudaStreamSynchronize(S0.stream));
+    }
+    std::memcpy(D_host, pinD, sizeof(float) * nq * k);
+    std::memcpy(I_host, pinI, sizeof(int64_t) * nq * k);
+    return B2F_OK;
   }
   for (int g = 0; g < G; ++g) {
     Shard& S = idx->shards[g];
@@ -1016,14 +1128,12 @@ int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_
       CU_TRY(cudaMemcpyPeerAsync(W.Dp + per * g, S0.dev, S.ws.D, S.dev, sizeof(float) * per, S0.stream));
       CU_TRY(cudaMemcpyPeerAsync(W.Ip + per * g, S0.dev, S.ws.I, S.dev, sizeof(int64_t) * per, S0.stream));
     }
-    merge_kernel<<<static_cast<int>(nq), 256, 0, S0.stream>>>(W.Dp, W.Ip, G, nq, k, W.Dp + per * G, W.Ip + per * G);
+    merge_kernel<<<static_cast<int>(nq), 256, 0, S0.stream>>>(W.Dp, W.Ip, G, nq, k, W.Dp + per * G, W.Ip + per * G, per, per, nullptr);
     CU_TRY(cudaGetLastError());
     idx->stats.launches += 1;
     Dres = W.Dp + per * G;
     Ires = W.Ip + per * G;
   }
-  float* pinD = reinterpret_cast<float*>(S0.ws.pin);
-  int64_t* pinI = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(S0.ws.pin) + d_off);
   CU_TRY(cudaMemcpyAsync(pinD, Dres, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
   CU_TRY(cudaMemcpyAsync(pinI, Ires, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
   CU_TRY(cudaStreamSynchronize(S0.stream));
@@ -1034,7 +1144,9 @@ int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_
 
 int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
   if (!idx || !key) return fail(B2F_ERR_INVALID, "bad option arguments");
+  B2F_TRY(settle_pending(idx));
   const std::string k(key);
+  if (k == "reset_stats") { reset_stats(idx); return B2F_OK; }
   if (k == "path") {
     if (value < 0 || value > 3) return fail(B2F_ERR_INVALID, "path must be 0..3");
     idx->path = static_cast<int>(value);
@@ -1057,7 +1169,8 @@ int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
     if (value < 0 || value > 2) return fail(B2F_ERR_INVALID, "umma_variant must be 0 (auto), 1 (SS) or 2 (TS)");
     idx->umma_variant = static_cast<int>(value);
   } else if (k == "l2_prefetch") {
-    idx->l2_prefetch = value ? 1 : 0;
+    if (value < 0 || value > 8) return fail(B2F_ERR_INVALID, "l2_prefetch must be 0 (off) or a distance of 1..8 tiles");
+    idx->l2_prefetch = static_cast<int>(value);
   } else if (k == "tighten") {
     if (value < 0 || value > 1000000) return fail(B2F_ERR_INVALID, "tighten must be 0 (off) or a pause in ns <= 1e6");
     idx->tighten = static_cast<int>(value);
@@ -1086,6 +1199,10 @@ int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
   else if (k == "score_launches") *out = s.score_launches;
   else if (k == "score_rows") *out = s.score_rows;
   else if (k == "select_ms") *out = s.select_ms;
+  else if (k == "merge_saw_overflow") {   // read-and-clear; meaningful after the stream has been synchronised
+    *out = idx->merge_flag_host ? static_cast<double>(*idx->merge_flag_host) : 0.0;
+    if (idx->merge_flag_host) *idx->merge_flag_host = 0;
+  }
   else return fail(B2F_ERR_INVALID, "unknown stat '" + k + "'");
   return B2F_OK;
 }

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kSelThreads) rescore_kernel(
 __global__ void __launch_bounds__(kSelThreads) final_kernel(
     uint64_t* __restrict__ cand_cur, uint64_t* __restrict__ cand_other, const int* __restrict__ cnt,
     int C, int k, const Seg* __restrict__ segs, int nseg, const int64_t* __restrict__ idmap,
-    float* __restrict__ D_out, int64_t* __restrict__ I_out, int64_t out_stride) {
+    float* __restrict__ D_out, int64_t* __restrict__ I_out, int64_t out_stride, const int* __restrict__ ovf) {
   __shared__ SelectSmem sm;
   __shared__ uint64_t sortbuf[kSortCap];
   const int q = blockIdx.x;
@@ -320,6 +320,8 @@ __global__ void __launch_bounds__(kSelThreads) final_kernel(
     D_out[static_cast<int64_t>(q) * out_stride + i] = s;
     I_out[static_cast<int64_t>(q) * out_stride + i] = id;
   }
+  __syncthreads();
+  if (threadIdx.x == 0 && ovf != nullptr && ovf[q] != 0) I_out[static_cast<int64_t>(q) * out_stride] = -2;  // see finalize_kernel
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -500,16 +502,26 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
     D_out[static_cast<int64_t>(q) * out_stride + i] = s;
     I_out[static_cast<int64_t>(q) * out_stride + i] = id;
   }
-  if (tid == 0 && ovf_out) ovf_out[q] = (ovf[q] != 0 || m2_all > S) ? 1 : 0;
+  if (tid == 0) {
+    const bool bad = ovf[q] != 0 || m2_all > S;
+    if (ovf_out) ovf_out[q] = bad ? 1 : 0;
+    // in-band marker for the sharded layout: a row whose list overflowed carries id -2 in its first
+    // slot until the exact engine has re-run it; merge_kernel reports it to every rank
+    if (bad) I_out[static_cast<int64_t>(q) * out_stride] = -2;
+  }
 }
 
 // Cross-shard merge: parts [G][nq][k] (each sorted by score desc, padded with id = -1) -> [nq][k].
 // Rank-by-counting: an element's output position is its position in its own list plus, for every
 // other list, the number of elements that precede it; ties go to the earlier part, then the earlier
 // position (the reference's merge keeps the earlier block on `>=`, :218).
+// Part g starts at Dp + g*strideD floats / Ip + g*strideI int64s (nq*k for two dense arrays; the
+// packed [D | I] records gathered over NCCL use the packed part size).
 __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ Dp,
                                                     const int64_t* __restrict__ Ip, int G, int64_t nq,
-                                                    int k, float* __restrict__ D, int64_t* __restrict__ I) {
+                                                    int k, float* __restrict__ D, int64_t* __restrict__ I,
+                                                    int64_t strideD, int64_t strideI,
+                                                    int* __restrict__ saw_overflow /* mapped host int or null */) {
   const int64_t q = blockIdx.x;
   __shared__ int total_valid;
   if (threadIdx.x == 0) total_valid = 0;
@@ -517,21 +529,24 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ Dp
   const int E = G * k;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     const int g = e / k, i = e - g * k;
-    const int64_t base = (static_cast<int64_t>(g) * nq + q) * k;
-    const int64_t id = Ip[base + i];
+    const int64_t baseD = static_cast<int64_t>(g) * strideD + q * k;
+    const int64_t baseI = static_cast<int64_t>(g) * strideI + q * k;
+    const int64_t id = Ip[baseI + i];
+    if (id == -2 && saw_overflow != nullptr) *saw_overflow = 1;   // a shard's list overflowed: result pending its re-run
     if (id < 0) continue;
     atomicAdd(&total_valid, 1);
-    const float s = Dp[base + i];
+    const float s = Dp[baseD + i];
     int rank = i;
     for (int g2 = 0; g2 < G; ++g2) {
       if (g2 == g) continue;
-      const int64_t b2 = (static_cast<int64_t>(g2) * nq + q) * k;
+      const int64_t b2D = static_cast<int64_t>(g2) * strideD + q * k;
+      const int64_t b2I = static_cast<int64_t>(g2) * strideI + q * k;
       // count valid elements of list g2 that precede (s): score > s, or == s when g2 < g
       int lo = 0, hi = k;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const bool valid = Ip[b2 + mid] >= 0;
-        const float s2 = Dp[b2 + mid];
+        const bool valid = Ip[b2I + mid] >= 0;
+        const float s2 = Dp[b2D + mid];
         const bool before = valid && (s2 > s || (s2 == s && g2 < g));
         if (before) lo = mid + 1; else hi = mid;
       }

@@ -33,7 +33,7 @@ struct UmmaSsArgs {
   int n_cols;                 // MMA N: padded query count, multiple of 16, 16..192
   int nq;                     // valid queries (<= n_cols)
   int stages;                 // smem ring depth
-  int prefetch;               // 1: TMA-prefetch the next tile into L2
+  int prefetch;               // D > 0: keep the TMA L2 prefetch D tiles ahead of the ring; 0: off
   int dense;                  // 1: store every score at slot (row - dense_row0)
   int64_t dense_row0;
   uint64_t* cand;             // [nq][C] flat lists
@@ -138,20 +138,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     // little to cover HBM latency at full bandwidth.  The producer therefore asks the TMA unit to
     // pull the NEXT tile of this CTA into L2 (12 contiguous 16 KB chunks) while it loads the current
     // one, so the ring only has to cover L2 latency.
-    auto prefetch_tile = [&](int tile) {
+    // a.prefetch = D > 0: stay D tiles ahead.  The D tiles after the first are requested up front; then
+    // every ring stage of tile i also requests one 16 KB chunk of tile i + D, so the requests are spread
+    // evenly over the stream instead of arriving in bursts of 12.
+    auto prefetch_chunk = [&](int tile, int j) {
       if (tile >= a.tile_end) return;
       const int t32 = (tile * 2 + static_cast<int>(cta_rank)) * (kSsTileRowsCta / kShadowTileRows);
-#pragma unroll 1
-      for (int j = 0; j < (kSsTileRowsCta / kShadowTileRows) * 3; ++j)   // 3 chunks of 4 K-blocks per 32-row tile
-        tma_prefetch_2d(&tmap_pf, 0, (t32 * kNumKBlocks + j * 4) * kShadowTileRows);
+      tma_prefetch_2d(&tmap_pf, 0, (t32 * kNumKBlocks + j * 4) * kShadowTileRows);
     };
-    if (a.prefetch) prefetch_tile(a.tile_begin + pair);
+    const int pfd = a.prefetch;
+    for (int d = 0; d < pfd; ++d)
+      for (int j = 0; j < kNumKBlocks; ++j) prefetch_chunk(a.tile_begin + pair + d * npairs, j);
     for (int tile = a.tile_begin + pair; tile < a.tile_end; tile += npairs) {
-      if (a.prefetch) prefetch_tile(tile + npairs);
       // shadow layout (common.cuh): this CTA's 128 rows are 4 consecutive 32-row tiles; K-block kb
       // of each is a contiguous 4 KB piece -> 4 TMA boxes per 16 KB stage
       const int t32 = (tile * 2 + static_cast<int>(cta_rank)) * (kSsTileRowsCta / kShadowTileRows);
       for (int kb = 0; kb < kNumKBlocks; ++kb) {
+        if (pfd) prefetch_chunk(tile + pfd * npairs, kb);
         mbar_wait(bar_empty + 8 * stage, phase ^ 1u, a.err);
         const uint32_t full_leader = mapa_u32(bar_full + 8 * stage, 0);
         if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2u * kSsStageBytes);

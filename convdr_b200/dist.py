@@ -2,8 +2,8 @@
 
 The collection is row-sharded across the ranks of a `torch.distributed` group (NCCL over
 NVLink/NVSwitch on the GPU box, gloo in the CPU tests); the queries are replicated; every rank
-computes its local top-k with global ids; ONE all-gather of the tiny `[nq, k]` (score, id) lists
-follows, and a device k-way merge kernel produces the global top-k on every rank.
+computes its local top-k with global ids; ONE all-gather of the tiny packed `[nq, k]` (score, id)
+lists follows, and a device k-way merge kernel produces the global top-k on every rank.
 
 This replaces FAISS's `IndexShards` (host threads + PCIe + CPU merge) that the reference builds with
 `index_cpu_to_gpu_multiple(..., shard=True)` (drivers/run_convdr_inference.py:355-368).
@@ -39,7 +39,6 @@ class ShardedFlatIP:
         self._local_search = local_search or (lambda q, k: self.index.search_device(q, k))
         self._merge = merge or (lambda Dp, Ip: self.index.merge_device(Dp, Ip))
         self.ntotal = 0
-        self._Dg = self._Ig = None
 
     # -- building -------------------------------------------------------------------------------
     def add_synthetic(self, n_total: int, seed: int = 0, stream: int = 0, norm: float = 1.0, chunk: int = 1 << 22):
@@ -63,21 +62,69 @@ class ShardedFlatIP:
         return lo, hi
 
     # -- searching ------------------------------------------------------------------------------
+    def _buffers(self, nq: int, k: int, device):
+        """Packed exchange buffers: one part = [D float32 [nq,k] | pad to 16 B | I int64 [nq,k]]."""
+        key = (nq, k, str(device))
+        if getattr(self, "_key", None) != key:
+            i_off = (nq * k * 4 + 15) // 16 * 16
+            part = i_off + nq * k * 8
+            send = torch.empty(part, dtype=torch.uint8, device=device)
+            recv = torch.empty((self.world, part), dtype=torch.uint8, device=device)
+            self._send, self._recv, self._i_off, self._part = send, recv, i_off, part
+            self._Dl = send[:nq * k * 4].view(torch.float32).view(nq, k)
+            self._Il = send[i_off:].view(torch.int64).view(nq, k)
+            self._key = key
+        return self._send, self._recv
+
     def search(self, q: torch.Tensor, k: int):
-        """q: [nq, 768] float32 on this rank's device (replicated).  Returns the global (D, I)."""
+        """q: [nq, 768] float32 on this rank's device (replicated).  Returns the global (D, I).
+
+        GPU ranks: local search, ONE all-gather of the packed (score, id) lists and the merge kernel
+        are queued on the engine's stream without a host round trip in between; the host waits once,
+        at the end (where the overflow flags of the local search are checked)."""
+        nq = q.shape[0]
+        if self.index is not None and q.is_cuda:
+            return self._search_cuda(q, k)
         D, I = self._local_search(q, k)
         if self.world == 1:
             return D, I
+        send, recv = self._buffers(nq, k, D.device)
+        self._Dl.copy_(D)
+        self._Il.copy_(I)
+        dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)
+        Dg = torch.stack([recv[w, :nq * k * 4].view(torch.float32).view(nq, k) for w in range(self.world)])
+        Ig = torch.stack([recv[w, self._i_off:].view(torch.int64).view(nq, k) for w in range(self.world)])
+        return self._merge(Dg, Ig)
+
+    def _search_cuda(self, q: torch.Tensor, k: int):
         nq = q.shape[0]
-        if self._Dg is None or self._Dg.shape != (self.world, nq, k) or self._Dg.device != D.device:
-            self._Dg = torch.empty((self.world, nq, k), dtype=torch.float32, device=D.device)
-            self._Ig = torch.empty((self.world, nq, k), dtype=torch.int64, device=D.device)
-        # concatenated-along-dim-0 form: accepted by both NCCL and gloo
-        dist.all_gather_into_tensor(self._Dg.view(self.world * nq, k), D.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(self._Ig.view(self.world * nq, k), I.contiguous(), group=self.group)
-        if D.is_cuda:
-            torch.cuda.current_stream(D.device).synchronize()  # the merge runs on the engine's stream
-        return self._merge(self._Dg, self._Ig)
+        idx = self.index
+        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        q = q.contiguous()
+        if self.world == 1:
+            idx.search_device_async(q, k, D, I)
+            idx.finish()
+            return D, I
+        send, recv = self._buffers(nq, k, q.device)
+        if getattr(self, "_ext", None) is None:
+            self._ext = torch.cuda.ExternalStream(idx.stream_ptr(0), device=q.device)
+        self._ext.wait_stream(torch.cuda.current_stream(q.device))     # q may have been produced there
+        with torch.cuda.stream(self._ext):
+            idx.search_device_async(q, k, self._Dl, self._Il)          # local top-k with global ids
+            dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)  # the only exchange (NCCL)
+            idx.merge_packed_device_async(recv, self.world, self._part, self._i_off, nq, k, D, I)
+        # One host wait.  A local query whose candidate list overflowed (adversarial data) is re-run by
+        # finish(); its rows travelled with the id -2 marker, which the merge kernel reports on EVERY
+        # rank (they all merge the same gathered bytes), so the decision to repeat the exchange is
+        # collective without an extra collective.
+        idx.finish()
+        if idx.stat("merge_saw_overflow") > 0:
+            with torch.cuda.stream(self._ext):
+                dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)
+                idx.merge_packed_device_async(recv, self.world, self._part, self._i_off, nq, k, D, I)
+            self._ext.synchronize()
+        return D, I
 
     def search_host(self, q_host, k: int, device=None):
         """End-to-end call with host buffers: pinned H2D of the queries, search, D2H of the result."""

@@ -152,6 +152,26 @@ class FlatIPIndex:
         _lib.check(_lib.load().b2f_search_device(self._ensure(), q.data_ptr(), q.shape[0], int(k), D.data_ptr(),
                                                  I.data_ptr()))
 
+    def search_device_async(self, q, k: int, D, I) -> None:
+        """Enqueue only (b2f_search_device_async): q, D, I are CUDA tensors that must stay alive until
+        `finish()`; later work on the index stream may consume D / I without a host round trip."""
+        _lib.check(_lib.load().b2f_search_device_async(self._ensure(), q.data_ptr(), q.shape[0], int(k),
+                                                       D.data_ptr(), I.data_ptr()))
+
+    def finish(self) -> None:
+        """Wait for every search enqueued with `search_device_async` (re-running overflowed queries)."""
+        if self._h is not None:
+            _lib.check(_lib.load().b2f_search_finish(self._h))
+
+    def merge_packed_device_async(self, parts, n_parts: int, part_bytes: int, i_offset: int, nq: int, k: int, D, I):
+        """Merge packed [D | I] parts (one all-gather's receive buffer, uint8) on the index stream."""
+        _lib.check(_lib.load().b2f_merge_packed_device_async(self._ensure(), parts.data_ptr(), int(n_parts),
+                                                             int(part_bytes), int(i_offset), int(nq), int(k),
+                                                             D.data_ptr(), I.data_ptr()))
+
+    def reset_stats(self) -> None:
+        self.set_option("reset_stats", 1)
+
     def merge_device(self, D_parts, I_parts):
         """Merge per-shard results [G, nq, k] (CUDA tensors on this index's device) into [nq, k]."""
         import torch

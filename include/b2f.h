@@ -100,6 +100,19 @@ int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_
 int b2f_search_device(b2f_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
                       int64_t* I_dev);
 
+/* Asynchronous form of b2f_search_device: only enqueues on the index stream and
+ * returns; up to 16 searches may be in flight.  Results (and q_dev, which must
+ * stay valid) may be consumed by later work on the same stream; the host may read
+ * them after b2f_search_finish(), which waits for the stream and re-runs, on
+ * the exact engine, any query whose candidate list overflowed (flags are written
+ * by the last kernel of a pass straight into mapped host memory).  Every other
+ * entry point settles pending searches first.  This is what lets a caller (the
+ * NCCL layout in convdr_b200/dist.py, bench.py) queue search -> all-gather ->
+ * merge, or several batches, without a host round trip in between.             */
+int b2f_search_device_async(b2f_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
+                            int64_t* I_dev);
+int b2f_search_finish(b2f_index* idx);
+
 /* Merge `n_parts` per-shard results [n_parts, nq, k] (device memory, each part
  * sorted descending, padded with -FLT_MAX / -1) into the global top-k
  * [nq, k] — the device-side replacement of the Python 2-way merge
@@ -107,6 +120,14 @@ int b2f_search_device(b2f_index* idx, const float* q_dev, int64_t nq, int k, flo
  * NCCL all-gather in the one-process-per-GPU layout.                           */
 int b2f_merge_device(b2f_index* idx, const float* D_parts_dev, const int64_t* I_parts_dev,
                      int n_parts, int64_t nq, int k, float* D_dev, int64_t* I_dev);
+
+/* Same merge, asynchronous (enqueued on the index stream), over PACKED parts as
+ * they arrive from ONE all-gather: part g occupies part_bytes bytes at
+ * parts_dev + g*part_bytes and holds D float32 [nq,k] at offset 0 and
+ * I int64 [nq,k] at offset i_offset_bytes (both multiples of 8).               */
+int b2f_merge_packed_device_async(b2f_index* idx, const void* parts_dev, int n_parts,
+                                  int64_t part_bytes, int64_t i_offset_bytes, int64_t nq, int k,
+                                  float* D_dev, int64_t* I_dev);
 
 /* faiss IndexFlat.reconstruct_n(i0, ni): copy stored rows [row0, row0+n) of shard
  * `shard` (shard-local positions) back to host memory — inspection / tests.    */
@@ -129,10 +150,15 @@ void* b2f_stream(b2f_index* idx, int shard);
  * "growth" (phase growth factor), "margin_ppm" (scale of the rigorous error
  * margin in parts-per-million, default 1000000), "keep_on_reset" (default 1),
  * "scan_max_auto" (largest batch AUTO sends to the SIMT scan, default 4),
- * "profile" (1: CUDA events around every scoring / selection launch).          */
+ * "profile" (1: CUDA events around every scoring / selection launch),
+ * "tighten" (TS tensor engine: in-kernel threshold tightening, pause of the
+ * refresher warp in ns; 0 = geometric phases), "umma_variant" (0 auto, 1 SS,
+ * 2 TS), "l2_prefetch" (SS variant: prefetch distance in tiles),
+ * "reset_stats" (any value: zero the counters below).                          */
 int b2f_set_option(b2f_index* idx, const char* key, int64_t value);
 
-/* Counters of the last search: "launches", "phases", "candidates",
+/* Counters since the last synchronous search started (asynchronous searches
+ * accumulate): "launches", "phases", "candidates",
  * "fallback_queries", "path", "passes"; with "profile" on also "score_ms",
  * "score_launches", "score_rows" (scoring kernels: device time, launches, rows
  * streamed) and "select_ms" (refresh + final kernels).                         */

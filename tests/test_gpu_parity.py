@@ -330,3 +330,80 @@ def test_auto_policy_and_invalid_arguments():
         idx.search(c_oracle.synth_block(0, 2, stream=1), 4096)   # k beyond the supported maximum
     with pytest.raises(AssertionError):
         idx.search(np.zeros((2, 100), dtype=np.float32), 5)
+
+
+def test_asynchronous_device_searches_in_flight_equal_synchronous_ones():
+    """b2f_search_device_async: 20 searches queued without a host wait (more than the 16 slots, and a
+    batch-size change that regrows the workspace in between) must equal the synchronous results."""
+    import torch
+    P = c_oracle.synth_block(0, 50000, seed=21)
+    idx = make_index("auto", P)
+    batches, outs = [], []
+    for i in range(20):
+        nq = 300 if i == 12 else 40 + i
+        q = torch.from_numpy(c_oracle.synth_block(0, nq, seed=100 + i, stream=1)).cuda()
+        D = torch.empty((nq, 30), dtype=torch.float32, device="cuda")
+        I = torch.empty((nq, 30), dtype=torch.int64, device="cuda")
+        idx.search_device_async(q, 30, D, I)
+        batches.append(q); outs.append((D, I))
+    idx.finish()
+    for q, (D, I) in zip(batches, outs):
+        Ds, Is = idx.search(q.cpu().numpy(), 30)
+        np.testing.assert_array_equal(I.cpu().numpy(), Is)
+        np.testing.assert_array_equal(D.cpu().numpy(), Ds)
+
+
+def test_packed_merge_and_overflow_marker():
+    """The packed [D | I] parts of the one-all-gather exchange merge like dense parts, and a part whose
+    candidate list overflowed travels with the id -2 marker that the merge kernel reports."""
+    import torch
+    P = c_oracle.synth_block(0, 60000, seed=22)
+    Q = c_oracle.synth_block(0, 13, seed=22, stream=1)
+    nq, k = Q.shape[0], 16
+    full = make_index("auto", P)
+    Dh, Ih = full.search(Q, k)
+    qd = torch.from_numpy(Q).cuda()
+    i_off = (nq * k * 4 + 15) // 16 * 16
+    part = i_off + nq * k * 8
+    recv = torch.zeros((3, part), dtype=torch.uint8, device="cuda")
+    subs = []
+    for g, (a, b) in enumerate([(0, 20000), (20000, 45000), (45000, 60000)]):
+        sub = make_index("auto")
+        sub.add_with_ids(P[a:b], np.arange(a, b, dtype=np.int64))
+        Dl = recv[g, :nq * k * 4].view(torch.float32).view(nq, k)
+        Il = recv[g, i_off:].view(torch.int64).view(nq, k)
+        sub.search_device_async(qd, k, Dl, Il)
+        sub.finish()
+        subs.append(sub)
+    Dm = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    Im = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    full.merge_packed_device_async(recv, 3, part, i_off, nq, k, Dm, Im)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(Im.cpu().numpy(), Ih)
+    np.testing.assert_array_equal(Dm.cpu().numpy(), Dh)
+    assert full.stat("merge_saw_overflow") == 0
+    recv[1, i_off:].view(torch.int64)[0] = -2            # what finalize_kernel writes for an overflowed row
+    full.merge_packed_device_async(recv, 3, part, i_off, nq, k, Dm, Im)
+    torch.cuda.synchronize()
+    assert full.stat("merge_saw_overflow") == 1
+    assert full.stat("merge_saw_overflow") == 0          # read-and-clear
+
+
+@pytest.mark.parametrize("path", ["umma_ts", "umma_ss", "scan_f32"])
+def test_overflowed_rows_carry_the_marker_until_rerun(path):
+    """All-equal scores overflow every list: the asynchronous call leaves id -2 in the first slot of
+    such rows; finish() re-runs them on the exact engine and the marker is gone."""
+    import torch
+    row = c_oracle.synth_block(0, 1, seed=2)
+    P = np.tile(row, (60000, 1))
+    Q = c_oracle.synth_block(0, 3, seed=2, stream=1)
+    idx = make_index(path, P)
+    qd = torch.from_numpy(Q).cuda()
+    D = torch.empty((3, 25), dtype=torch.float32, device="cuda")
+    I = torch.empty((3, 25), dtype=torch.int64, device="cuda")
+    idx.search_device_async(qd, 25, D, I)
+    torch.cuda.synchronize()
+    assert I[:, 0].tolist() == [-2, -2, -2]
+    idx.finish()
+    assert I.cpu().tolist() == [list(range(25))] * 3
+    assert idx.stat("fallback_queries") == 3
