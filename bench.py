@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="tensor engine variant: 0 auto, 1 SS, 2 TS")
     ap.add_argument("--l2-prefetch", type=int, default=1)
     ap.add_argument("--tighten", type=int, default=-1, help="-1 engine default, 0 off, >0 refresher pause in ns")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (A/B experiments)")
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
@@ -206,7 +207,19 @@ def run_b2f_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", init_method="env://", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator comes up; stdout carries ONE
+        # JSON line, so the banner goes to stderr (fd-level redirect, NCCL writes from C).
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", init_method="env://", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     n_gpus = world
 
     index = FlatIPIndex(D, devices=[local_rank])
@@ -218,6 +231,9 @@ def run_b2f_arm(args):
     index.set_option("l2_prefetch", args.l2_prefetch)
     if args.tighten >= 0:
         index.set_option("tighten", args.tighten)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        index.set_option(key, int(val))
     sharded = ShardedFlatIP(index=index)
     t0 = time.perf_counter()
     lo, hi = sharded.add_synthetic(args.rows, seed=0, stream=0)
@@ -239,13 +255,12 @@ def run_b2f_arm(args):
     Id = torch.empty((nq, k), dtype=torch.int64, device=dev)
 
     def step_device():
-        # N = 1: the device-resident call is asynchronous (b2f_search_device_async): the K searches of
-        # the timed region are queued back to back and settled once, inside the region, by finish().
-        # N > 1: local search -> ONE NCCL all-gather -> merge kernel, one host wait per step.
-        if world == 1:
-            index.search_device_async(q_dev, k, Dd, Id)
-            return Dd, Id
-        return sharded.search(q_dev, k)
+        # The device-resident call is asynchronous: local search (b2f_search_device_async), and for N > 1
+        # ONE NCCL all-gather of the packed lists + the merge kernel, all queued on the engine's stream.
+        # The K searches of the timed region are queued back to back and settled once, inside the
+        # region, by finish() (stream wait + overflow flags of every queued search).
+        sharded.search_async(q_dev, k, Dd, Id)
+        return Dd, Id
 
     # ---- device-resident timing ----
     sampler = ClockSampler()
@@ -253,7 +268,7 @@ def run_b2f_arm(args):
         sampler.start()          # nvidia-smi needs ~100 ms to start: begin before the warm-up
     for _ in range(max(args.warmup, 3)):
         Dd, Id = step_device()
-    index.finish()
+    sharded.finish()
     engine_path = int(index.stat("path"))
     barrier()
     index.reset_stats()
@@ -262,7 +277,10 @@ def run_b2f_arm(args):
     ev0.record(stream)
     for _ in range(args.steps):
         Dd, Id = step_device()
-    index.finish()               # waits for the stream and checks the overflow flags of every queued search
+    clean = sharded.finish()     # waits for the stream and checks the overflow flags of every queued search
+    if not clean:                # a list overflowed on some rank (never on this data): repeat synchronously, timed
+        for _ in range(args.steps):
+            Dd, Id = sharded.search(q_dev, k)
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)

@@ -114,6 +114,7 @@ struct Workspace {
   float* q32 = nullptr;
   __nv_bfloat16* q16 = nullptr;
   float* qnorm = nullptr;
+  float* qerr = nullptr;      // [nq] upper bound of ||q - bf16(q)||
   int* ovf_all = nullptr;
   int* ovf_host = nullptr;  // pinned
   // per-shard results of one search
@@ -164,7 +165,7 @@ struct Shard {
   float* x32 = nullptr;
   __nv_bfloat16* x16 = nullptr;
   int64_t n = 0, cap = 0;
-  unsigned int* maxnorm2 = nullptr;  // device, float bits
+  unsigned int* maxnorm2 = nullptr;  // device, float bits: [0] max ||p||^2, [1] max ||p - bf16(p)||^2
   int64_t* idmap = nullptr;          // optional explicit labels [cap]
   bool has_ids = false;
   std::vector<Seg> segs;
@@ -197,6 +198,7 @@ struct b2f_index {
   int profile = 0;
   int umma_variant = 0;   // 0 auto, 1 smem-stationary queries (SS), 2 TMEM-stationary queries (TS)
   int l2_prefetch = 1;
+  int worst_case_margin = 0;  // 1: bf16 margin from the data-independent worst case (A/B only)
   int tighten = 400;      // TS engine: in-kernel threshold tightening through a global hit histogram (one
                           // launch after the bootstrap); pause of the refresher between rounds in ns,
                           // 0 = off (geometric phases with a refresh kernel between them).
@@ -293,12 +295,13 @@ int ingest_rows(b2f_index* idx, Shard& S, int64_t n) {
 int ensure_query_ws(Shard& S, int64_t nq, int k) {
   Workspace& W = S.ws;
   if (nq > W.nq_cap) {
-    dev_free(W.q32); dev_free(W.q16); dev_free(W.qnorm);
+    dev_free(W.q32); dev_free(W.q16); dev_free(W.qnorm); dev_free(W.qerr);
     if (W.ovf_host) { cudaFreeHost(W.ovf_host); W.ovf_host = nullptr; W.ovf_all = nullptr; }
     const int64_t cap = std::max<int64_t>(nq, 256);
     B2F_TRY(dev_alloc(&W.q32, static_cast<size_t>(cap) * kD));
     B2F_TRY(dev_alloc(&W.q16, static_cast<size_t>(cap + kUmmaMaxQ + 16) * kD));
     B2F_TRY(dev_alloc(&W.qnorm, static_cast<size_t>(cap + kUmmaMaxQ + 16)));
+    B2F_TRY(dev_alloc(&W.qerr, static_cast<size_t>(cap + kUmmaMaxQ + 16)));
     // per-query overflow flags live in mapped pinned host memory: the last kernel of a pass writes them
     // straight to the host (no copy operation on the stream), the host reads them after the sync
     CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&W.ovf_host), static_cast<size_t>(cap) * kMaxPending * sizeof(int),
@@ -364,13 +367,34 @@ int ensure_pin(Shard& S, size_t bytes) {
 
 // Start of a pass, one block per query: the prefilter margin 2*eps_q = 2u * ||q|| * max||p|| (rounded
 // up) and the zeroing of the pass state (one launch instead of three memsets and a kernel).
-__global__ void pass_init_kernel(const float* __restrict__ qnorm, const unsigned int* __restrict__ maxnorm2_bits,
-                                 float two_u, float* __restrict__ margin, int* __restrict__ cnt,
+//   mode 0 (exact engine): margin 0.
+//   mode 1 (fp32 scan):    eps = u_scan * ||q|| * P,  P = max ||p||   (Cauchy-Schwarz on sum |q_t p_t|).
+//   mode 2 (bf16 tensor):  s~ = fl(sum q^_t p^_t) with q^ = bf16(q), p^ = bf16(p).  Then
+//       |s~ - s| <= |sum q^ (p^ - p)| + |sum (q^ - q) p| + accumulation
+//                <= (1 + 2^-9) ||q|| E + e_q P + g ||q|| P,
+//     E = max ||p - p^|| (kept per shard at add time), e_q = ||q - q^||, g = 1.1e-4 >= 768 * 2^-23
+//     (fp32 accumulation of 768 exact products inside the tensor core, truncation allowed).
+// Every factor is an upper bound and every operation rounds up; `scale` (margin_ppm) multiplies the result.
+__global__ void pass_init_kernel(const float* __restrict__ qnorm, const float* __restrict__ qerr,
+                                 const unsigned int* __restrict__ maxnorm2_bits, int mode, float scale, float u_scan,
+                                 float* __restrict__ margin, int* __restrict__ cnt,
                                  int* __restrict__ ovf, int* __restrict__ cnt2, int max_pairs) {
   const int q = blockIdx.x;
   if (threadIdx.x == 0) {
-    const float pn = __fsqrt_ru(__uint_as_float(*maxnorm2_bits));
-    margin[q] = __fmul_ru(__fmul_ru(qnorm[q], pn), two_u);
+    const float P = __fsqrt_ru(__uint_as_float(maxnorm2_bits[0]));
+    float eps = 0.f;
+    if (mode == 1) {
+      eps = __fmul_ru(__fmul_ru(qnorm[q], P), u_scan);
+    } else if (mode == 3) {   // worst-case bf16 bound 2^-8 * 1.002 + 1e-4 (A/B reference for mode 2)
+      eps = __fmul_ru(__fmul_ru(qnorm[q], P), 0.004014063f);
+    } else if (mode == 2) {
+      const float E = __fsqrt_ru(__uint_as_float(maxnorm2_bits[1]));
+      const float a = __fmul_ru(__fmul_ru(qnorm[q], E), 1.001953125f);
+      const float b = __fmul_ru(qerr[q], P);
+      const float c = __fmul_ru(__fmul_ru(qnorm[q], P), 1.1e-4f);
+      eps = __fadd_ru(__fadd_ru(a, b), c);
+    }
+    margin[q] = __fmul_ru(__fmul_ru(eps, 2.0f), scale);
     cnt[q] = 0;
     ovf[q] = 0;
   }
@@ -411,12 +435,10 @@ void collect_prof(b2f_index* idx, Shard& S) {
   P.used = 0;
 }
 
-// Rigorous worst-case error of a score computed from rounded operands / in reduced precision,
-// relative to ||q|| * ||p|| (Cauchy-Schwarz on sum |q_t p_t|):
-//   bf16 engine: two round-to-nearest bf16 operands (2 * 2^-9 + 2^-18) + fp32 accumulation of 768
-//                exact products inside the tensor core (<= 768 * 2^-23) -> 0.004014
-//   fp32 scan  : 24 sequential fma + 5 tree adds, one rounding each -> 29 * 2^-24 < 2^-19
-constexpr double kUBf16 = 0.00390625 * 1.002 + 1.0e-4;
+// Rigorous error bounds of the prefilter scores (see pass_init_kernel for the bf16 tensor engine,
+// whose bound is data-dependent: max ||p - bf16(p)|| is kept per shard at add time):
+//   fp32 scan  : 24 sequential fma + 5 tree adds, one rounding each -> 29 * 2^-24 < 2^-19, relative to
+//                ||q|| * ||p|| (Cauchy-Schwarz on sum |q_t p_t|)
 constexpr double kUScan = 1.9073486328125e-06;
 
 struct PassPlan {
@@ -476,7 +498,7 @@ PassPlan make_plan(const b2f_index* idx, const Shard& S, int path, int k, int64_
 // [nqp,768]; q16p: their bf16 copies padded with zero rows (tensor path).  Results go to
 // D_out/I_out with row stride out_stride.
 int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q32p, const __nv_bfloat16* q16p,
-                 const float* qnormp, int nqp, int k, float* D_out, int64_t* I_out, int64_t out_stride,
+                 const float* qnormp, const float* qerrp, int nqp, int k, float* D_out, int64_t* I_out, int64_t out_stride,
                  int* ovf_dst) {
   Workspace& W = S.ws;
   Stats& st = idx->stats;
@@ -494,10 +516,10 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   } else {
     W.areas_clean = false;  // flat lists overwrite the private areas
   }
-  const double u = plan.path == B2F_PATH_UMMA_BF16 ? kUBf16 : kUScan;
-  const float two_u = plan.exact ? 0.f : static_cast<float>(2.0 * u * (idx->margin_ppm * 1e-6) * 1.0000001);
-  pass_init_kernel<<<nqp, 128, 0, s>>>(qnormp, S.maxnorm2, two_u, W.margin, W.cnt, W.ovf,
-                                       tensor ? W.cnt2 : nullptr, S.max_pairs);
+  const int margin_mode = plan.exact ? 0 : (plan.path == B2F_PATH_UMMA_BF16 ? (idx->worst_case_margin ? 3 : 2) : 1);
+  pass_init_kernel<<<nqp, 128, 0, s>>>(qnormp, qerrp, S.maxnorm2, margin_mode,
+                                       static_cast<float>(idx->margin_ppm * 1e-6 * 1.0000001), static_cast<float>(kUScan),
+                                       W.margin, W.cnt, W.ovf, tensor ? W.cnt2 : nullptr, S.max_pairs);
   st.launches += 1;
 
   int cur = 0;
@@ -659,7 +681,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
   B2F_TRY(upload_segs(S));
   const int64_t nq_pad = round_up(nq, 16) + kUmmaMaxQ;
   prep_queries_kernel<<<static_cast<int>((nq_pad * 32 + 127) / 128), 128, 0, s>>>(
-      q_d, static_cast<int>(nq), static_cast<int>(nq_pad), W.q16, W.qnorm);
+      q_d, static_cast<int>(nq), static_cast<int>(nq_pad), W.q16, W.qnorm, W.qerr);
   CU_TRY(cudaGetLastError());
   idx->stats.launches += 1;
   if (plan.path == B2F_PATH_UMMA_BF16) {
@@ -680,7 +702,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
   }
   for (int64_t q0 = 0; q0 < nq; q0 += plan.qp) {
     const int nqp = static_cast<int>(std::min<int64_t>(plan.qp, nq - q0));
-    B2F_TRY(enqueue_pass(idx, S, plan, q_d + q0 * kD, W.q16 + q0 * kD, W.qnorm + q0, nqp, k, D_d + q0 * k,
+    B2F_TRY(enqueue_pass(idx, S, plan, q_d + q0 * kD, W.q16 + q0 * kD, W.qnorm + q0, W.qerr + q0, nqp, k, D_d + q0 * k,
                          I_d + q0 * k, k, ovf_slot + q0));
   }
   return B2F_OK;
@@ -716,7 +738,7 @@ int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k,
     for (int i = 0; i < nb; ++i)
       CU_TRY(cudaMemcpyAsync(W.fbq + static_cast<size_t>(i) * kD, q_d + bad[b0 + i] * kD, kD * 4,
                              cudaMemcpyDeviceToDevice, s));
-    B2F_TRY(enqueue_pass(idx, S, plan, W.fbq, nullptr, W.qnorm /*unused: exact*/, nb, k, W.fbD, W.fbI, k, nullptr));
+    B2F_TRY(enqueue_pass(idx, S, plan, W.fbq, nullptr, W.qnorm /*unused: exact*/, W.qerr, nb, k, W.fbD, W.fbI, k, nullptr));
     for (int i = 0; i < nb; ++i) {
       CU_TRY(cudaMemcpyAsync(D_d + bad[b0 + i] * k, W.fbD + static_cast<size_t>(i) * k, sizeof(float) * k,
                              cudaMemcpyDeviceToDevice, s));
@@ -804,8 +826,8 @@ int b2f_create(int d, const int* devices, int n_dev, b2f_index** out) {
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&S.maxnorm2), sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(S.maxnorm2, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&S.maxnorm2), 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(S.maxnorm2, 0, 2 * sizeof(unsigned int));
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       std::string m = std::string("device setup failed: ") + cudaGetErrorString(e);
@@ -851,7 +873,7 @@ void b2f_destroy(b2f_index* idx) {
     dev_free(W.cand[0]); dev_free(W.cand[1]); dev_free(W.cnt); dev_free(W.tau); dev_free(W.tauP);
     dev_free(W.ovf); dev_free(W.margin); dev_free(W.err); dev_free(W.q32); dev_free(W.q16);
     dev_free(W.gath); dev_free(W.cnt2); dev_free(W.hist); dev_free(W.hkey0); dev_free(W.hshift);
-    dev_free(W.qnorm); dev_free(W.D); dev_free(W.I); dev_free(W.Dp); dev_free(W.Ip);
+    dev_free(W.qnorm); dev_free(W.qerr); dev_free(W.D); dev_free(W.I); dev_free(W.Dp); dev_free(W.Ip);
     dev_free(W.fbq); dev_free(W.fbD); dev_free(W.fbI);
     if (W.ovf_host) cudaFreeHost(W.ovf_host);
     if (W.pin) cudaFreeHost(W.pin);
@@ -992,7 +1014,7 @@ int b2f_reset(b2f_index* idx) {
     S.n = 0;
     S.segs.clear();
     S.has_ids = false;
-    CU_TRY(cudaMemsetAsync(S.maxnorm2, 0, sizeof(unsigned int), S.stream));
+    CU_TRY(cudaMemsetAsync(S.maxnorm2, 0, 2 * sizeof(unsigned int), S.stream));
     if (!idx->keep_on_reset) {
       dev_free(S.x32); dev_free(S.x16); dev_free(S.idmap);
       S.cap = 0;
@@ -1174,6 +1196,8 @@ int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
   } else if (k == "tighten") {
     if (value < 0 || value > 1000000) return fail(B2F_ERR_INVALID, "tighten must be 0 (off) or a pause in ns <= 1e6");
     idx->tighten = static_cast<int>(value);
+  } else if (k == "worst_case_margin") {
+    idx->worst_case_margin = value ? 1 : 0;
   } else if (k == "profile") {
     idx->profile = value ? 1 : 0;
   } else if (k == "scan_max_auto") {

@@ -96,16 +96,15 @@ class ShardedFlatIP:
         Ig = torch.stack([recv[w, self._i_off:].view(torch.int64).view(nq, k) for w in range(self.world)])
         return self._merge(Dg, Ig)
 
-    def _search_cuda(self, q: torch.Tensor, k: int):
+    def search_async(self, q: torch.Tensor, k: int, D: torch.Tensor, I: torch.Tensor) -> None:
+        """Queue local search -> all-gather -> merge on the engine's stream and return; `finish()`
+        settles.  q, D, I (CUDA tensors) must stay alive; consecutive calls reuse the exchange buffers
+        in stream order."""
         nq = q.shape[0]
         idx = self.index
-        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
-        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
-        q = q.contiguous()
         if self.world == 1:
             idx.search_device_async(q, k, D, I)
-            idx.finish()
-            return D, I
+            return
         send, recv = self._buffers(nq, k, q.device)
         if getattr(self, "_ext", None) is None:
             self._ext = torch.cuda.ExternalStream(idx.stream_ptr(0), device=q.device)
@@ -114,6 +113,25 @@ class ShardedFlatIP:
             idx.search_device_async(q, k, self._Dl, self._Il)          # local top-k with global ids
             dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)  # the only exchange (NCCL)
             idx.merge_packed_device_async(recv, self.world, self._part, self._i_off, nq, k, D, I)
+        self._last = (q, k, D, I)
+
+    def finish(self) -> bool:
+        """Wait for the queued searches.  Returns False if a candidate list overflowed on some rank
+        (every rank sees the same answer): the caller must repeat those searches synchronously."""
+        self.index.finish()
+        return not (self.world > 1 and self.index.stat("merge_saw_overflow") > 0)
+
+    def _search_cuda(self, q: torch.Tensor, k: int):
+        nq = q.shape[0]
+        idx = self.index
+        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        q = q.contiguous()
+        self.search_async(q, k, D, I)
+        if self.world == 1:
+            idx.finish()
+            return D, I
+        send, recv = self._send, self._recv
         # One host wait.  A local query whose candidate list overflowed (adversarial data) is re-run by
         # finish(); its rows travelled with the id -2 marker, which the merge kernel reports on EVERY
         # rank (they all merge the same gathered bytes), so the decision to repeat the exchange is

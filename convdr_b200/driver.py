@@ -16,25 +16,18 @@ are libb2f kernels.  The array bookkeeping of the reference's Python merge is ke
 from __future__ import annotations
 
 import logging
-import os
-import pickle
 import time
 
 import numpy as np
 
 logger = logging.getLogger(__name__)
 
-EMB_NAME = "passage__emb_p__data_obj_%d.pb"      # utils/util.py:108-109 + gen_passage_embeddings.py:158
-EMBID_NAME = "passage__embid_p__data_obj_%d.pb"  # gen_passage_embeddings.py:164
+from .blocks import EMB_NAME, EMBID_NAME, flat_shard_paths, load_flat_into, read_block  # noqa: F401
 
 
 def load_block(ann_data_dir: str, block_id: int):
     """Reader side of the per-rank pickle block format (reference :161-175).  Raises on failure."""
-    with open(os.path.join(ann_data_dir, EMB_NAME % block_id), "rb") as handle:
-        emb = pickle.load(handle)
-    with open(os.path.join(ann_data_dir, EMBID_NAME % block_id), "rb") as handle:
-        embid = pickle.load(handle)
-    return emb, embid
+    return read_block(ann_data_dir, block_id)
 
 
 def _merge_sorted(run_s, run_i, cur_s, cur_i, topN):
@@ -78,19 +71,26 @@ def search_one_by_one(ann_data_dir, gpu_index, query_embedding, topN, max_blocks
 def search_resident(ann_data_dir, index, query_embedding, topN, max_blocks: int = 8):
     """Load every block once (labels = the block's offsets), then a single exact search.
 
-    Returns (D float64 [nq, topN], I int64 [nq, topN]) — the first topN columns of what
-    `search_one_by_one` returns (up to the documented tie order), which is all `EvalDevQuery` reads.
+    Flat shards (`passage_shard_{b}.b2f`, convdr_b200/blocks.py) are preferred when present: they are
+    memory-mapped and streamed in chunks instead of unpickled whole.  Otherwise the reference's pickle
+    blocks are read.  Returns (D float64 [nq, topN], I int64 [nq, topN]) — the first topN columns of
+    what `search_one_by_one` returns (up to the documented tie order), which is all `EvalDevQuery`
+    reads.
     """
-    n_blocks = 0
     if index.ntotal == 0:
-        for block_id in range(max_blocks):
-            try:
-                emb, embid = load_block(ann_data_dir, block_id)
-            except FileNotFoundError:
-                break
-            index.add_with_ids(emb, np.asarray(embid, dtype=np.int64))
-            n_blocks += 1
-        if n_blocks == 0:
-            raise FileNotFoundError("no passage embedding block under " + str(ann_data_dir))
+        flat = flat_shard_paths(ann_data_dir, max_blocks)
+        if flat:
+            load_flat_into(index, flat)
+        else:
+            n_blocks = 0
+            for block_id in range(max_blocks):
+                try:
+                    emb, embid = load_block(ann_data_dir, block_id)
+                except FileNotFoundError:
+                    break
+                index.add_with_ids(emb, np.asarray(embid, dtype=np.int64))
+                n_blocks += 1
+            if n_blocks == 0:
+                raise FileNotFoundError("no passage embedding block under " + str(ann_data_dir))
     D, I = index.search(query_embedding, topN)
     return D.astype(np.float64), I

@@ -407,3 +407,23 @@ def test_overflowed_rows_carry_the_marker_until_rerun(path):
     idx.finish()
     assert I.cpu().tolist() == [list(range(25))] * 3
     assert idx.stat("fallback_queries") == 3
+
+
+def test_search_resident_over_flat_shards_matches_block_loop(tmp_path):
+    """blocks written in the reference's pickle format, converted once to flat shards,
+    streamed into the resident index in chunks; one search equals the reference's block loop."""
+    from convdr_b200 import blocks
+    n_total, W = 30011, 4
+    P = c_oracle.synth_block(0, n_total, seed=31)
+    Q = c_oracle.synth_block(0, 21, seed=31, stream=1)
+    for b in range(W):
+        off = blocks.strided_offsets(n_total, b, W)
+        blocks.write_block(str(tmp_path), b, P[off], off)
+    Do, Io = flat_ip.search_one_by_one(str(tmp_path), flat_ip.IndexFlatIP(768), Q, 40)
+    blocks.convert_blocks_to_flat(str(tmp_path))
+    idx = make_index("auto")
+    Dr, Ir = driver.search_resident(str(tmp_path), idx, Q, 40)
+    assert idx.ntotal == n_total
+    score_of = lambda qi, ids: Q[qi].astype(np.float64) @ P[ids].astype(np.float64).T
+    r = flat_ip.compare(Dr.astype(np.float32), Ir, Do[:, :40].astype(np.float32), Io[:, :40], score_of, rtol=RTOL)
+    assert r["violations"] == 0, r
