@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="tensor engine variant: 0 auto, 1 SS, 2 TS")
     ap.add_argument("--l2-prefetch", type=int, default=1)
     ap.add_argument("--tighten", type=int, default=-1, help="-1 engine default, 0 off, >0 refresher pause in ns")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: result exchange through the engine's peer-memory kernels (default) or ncclAllGather")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (A/B experiments)")
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -87,23 +89,89 @@ def ncu_traffic_per_launch(rows_per_launch: float):
 
 
 class ClockSampler:
+    """SM clock / power / throttle reasons of this rank's GPU, sampled through NVML from a thread
+    every ~2 ms (the timed region of a multi-GPU run lasts tens of milliseconds: a 20 ms nvidia-smi loop
+    cannot see it).  `mark()` brackets the timed region; only samples inside it are reported.  Falls back
+    to an `nvidia-smi -lms` subprocess when pynvml is unavailable."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self):
-        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, device_index: int = 0):
+        import threading
+        self.device_index = device_index
+        self.samples = []            # (t, sm_mhz, watts, reasons bitmask)
+        self.t0 = self.t1 = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.sm_max = None
         self.proc = None
+        self.tmp = None
+
+    def _run(self, nv, h):
+        while not self._stop.is_set():
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mw = nv.nvmlDeviceGetPowerUsage(h)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append((time.perf_counter(), float(clk), mw / 1000.0, int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        import threading
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.device_index
+            if vis:
+                ids = [x for x in vis.split(",") if x.strip() != ""]
+                if self.device_index < len(ids) and ids[self.device_index].strip().isdigit():
+                    phys = int(ids[self.device_index])
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, args=(nv, h), daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._thread = None
+        try:
+            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "20"], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Call right before and right after the timed region."""
+        if self.t0 is None:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            sel = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1]
+            out["source"] = "nvml, 2 ms period, samples inside the timed region"
+            if not sel:              # region shorter than one period: take the samples closest to it
+                sel = sorted(self.samples, key=lambda x: abs(x[0] - (self.t0 or 0)))[:3]
+                out["source"] = "nvml, nearest samples (timed region shorter than the sampling period)"
+            if sel:
+                mask = 0
+                for x in sel:
+                    mask |= x[3]
+                out.update({"sm_mhz": statistics.median(x[1] for x in sel), "sm_mhz_min": min(x[1] for x in sel),
+                            "sm_max_mhz": self.sm_max, "power_w_median": statistics.median(x[2] for x in sel),
+                            "reasons": sorted(name for bit, name in self.REASONS.items() if mask & bit),
+                            "samples": len(sel)})
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -129,6 +197,7 @@ class ClockSampler:
                     if val.lower().startswith("active"):
                         reasons.add(name)
         os.unlink(self.tmp.name)
+        out["source"] = "nvidia-smi -lms 20, samples above 250 W"
         if sm:
             out["sm_mhz"] = statistics.median(sm)
             out["sm_mhz_min"] = min(sm)
@@ -235,6 +304,10 @@ def run_b2f_arm(args):
         key, val = kv.split("=")
         index.set_option(key, int(val))
     sharded = ShardedFlatIP(index=index)
+    exchange = "none"
+    if world > 1:
+        exchange = "peer-memory kernels (CUDA IPC over NVLink)" if (args.exchange == "peer" and
+                   sharded.enable_peer_exchange(args.nq, args.k)) else "ncclAllGather + merge kernel"
     t0 = time.perf_counter()
     lo, hi = sharded.add_synthetic(args.rows, seed=0, stream=0)
     build_s = time.perf_counter() - t0
@@ -263,7 +336,7 @@ def run_b2f_arm(args):
         return Dd, Id
 
     # ---- device-resident timing ----
-    sampler = ClockSampler()
+    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()          # nvidia-smi needs ~100 ms to start: begin before the warm-up
     for _ in range(max(args.warmup, 3)):
@@ -274,6 +347,7 @@ def run_b2f_arm(args):
     index.reset_stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = score_ms = score_launches = score_rows = select_ms = 0.0
+    sampler.mark()
     ev0.record(stream)
     for _ in range(args.steps):
         Dd, Id = step_device()
@@ -283,6 +357,7 @@ def run_b2f_arm(args):
             Dd, Id = sharded.search(q_dev, k)
     ev1.record(stream)
     barrier()
+    sampler.mark()
     dev_ms = ev0.elapsed_time(ev1)
     launches, score_ms, score_launches = index.stat("launches"), index.stat("score_ms"), index.stat("score_launches")
     score_rows, select_ms = index.stat("score_rows"), index.stat("select_ms")
@@ -341,7 +416,7 @@ def run_b2f_arm(args):
                 "l2_policy": "inputs larger than L2 (>= 7 GB streamed per GPU per step vs 126 MB L2); no flush needed",
                 "engine_path": engine_path, "tensor_variant": args.variant, "l2_prefetch": args.l2_prefetch,
                 "build_seconds": round(build_s, 2),
-                "parallelism": f"shard{n_gpus}",
+                "parallelism": f"shard{n_gpus}", "exchange": exchange,
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -185,8 +185,21 @@ struct b2f_index {
   int d = kD;
   std::vector<Shard> shards;
   std::vector<Pending> pending;   // enqueued by b2f_search_device_async, settled by b2f_search_finish
-  int* merge_flag_host = nullptr; // mapped host int: a packed merge saw a part whose list had overflowed
-  int* merge_flag_dev = nullptr;
+  int* merge_flag_host = nullptr; // mapped host ints: [0] a merge saw a part whose list had overflowed,
+  int* merge_flag_dev = nullptr;  //                   [1] the peer exchange timed out waiting for a rank
+  // peer-memory exchange (one process per GPU; see kernels_select.cuh)
+  struct Xchg {
+    int rank = -1, world = 0;
+    int64_t max_nq = 0;
+    int max_k = 0;
+    size_t part_cap = 0, flags_off = 0, bytes = 0;
+    char* local = nullptr;                 // this rank's buffer [2][world][part_cap] + flags[2][world]
+    char* peer[kXchgMaxWorld] = {nullptr}; // the same buffer of every rank (peer[rank] == local)
+    char* stage = nullptr;                 // local packed part [D | I] written by the search
+    int* counter = nullptr;
+    unsigned int seq = 0;
+    bool connected = false;
+  } xchg;
   int64_t ntotal = 0;
   // options
   int path = B2F_PATH_AUTO;
@@ -839,13 +852,13 @@ int b2f_create(int d, const int* devices, int n_dev, b2f_index** out) {
   }
   {
     cudaSetDevice(idx->shards[0].dev);
-    if (cudaHostAlloc(reinterpret_cast<void**>(&idx->merge_flag_host), sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+    if (cudaHostAlloc(reinterpret_cast<void**>(&idx->merge_flag_host), 2 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&idx->merge_flag_dev), idx->merge_flag_host, 0) != cudaSuccess) {
       (void)cudaGetLastError();
       b2f_destroy(idx);
       return fail(B2F_ERR_CUDA, "mapped host allocation failed");
     }
-    *idx->merge_flag_host = 0;
+    idx->merge_flag_host[0] = idx->merge_flag_host[1] = 0;
   }
   // peer access between shard devices (direct NVLink copies for the result gather)
   for (size_t i = 0; i < devs.size(); ++i)
@@ -882,6 +895,14 @@ void b2f_destroy(b2f_index* idx) {
     if (S.stream) cudaStreamDestroy(S.stream);
   }
   if (idx->merge_flag_host) cudaFreeHost(idx->merge_flag_host);
+  if (idx->xchg.local) {
+    cudaSetDevice(idx->shards[0].dev);
+    for (int r = 0; r < idx->xchg.world; ++r)
+      if (r != idx->xchg.rank && idx->xchg.peer[r]) cudaIpcCloseMemHandle(idx->xchg.peer[r]);
+    cudaFree(idx->xchg.local);
+    cudaFree(idx->xchg.stage);
+    cudaFree(idx->xchg.counter);
+  }
   (void)cudaGetLastError();
   delete idx;
 }
@@ -1090,6 +1111,90 @@ int b2f_merge_packed_device_async(b2f_index* idx, const void* parts_dev, int n_p
   return B2F_OK;
 }
 
+int b2f_xchg_create(b2f_index* idx, int rank, int world, int64_t max_nq, int max_k, void* handle_out) {
+  if (!idx || !handle_out || world < 2 || world > kXchgMaxWorld || rank < 0 || rank >= world || max_nq < 1 ||
+      max_k < 1 || max_k > B2F_MAX_K)
+    return fail(B2F_ERR_INVALID, "bad exchange arguments (2 <= world <= 16)");
+  if (idx->shards.size() != 1) return fail(B2F_ERR_INVALID, "the peer exchange needs a single-shard index per process");
+  if (idx->xchg.local) return fail(B2F_ERR_INVALID, "exchange already created");
+  B2F_TRY(settle_pending(idx));
+  Shard& S = idx->shards[0];
+  CU_TRY(cudaSetDevice(S.dev));
+  auto& X = idx->xchg;
+  X.rank = rank; X.world = world; X.max_nq = max_nq; X.max_k = max_k;
+  X.part_cap = static_cast<size_t>(round_up(round_up(max_nq * max_k * 4, 16) + max_nq * max_k * 8, 128));
+  X.flags_off = 2 * static_cast<size_t>(world) * X.part_cap;
+  X.bytes = X.flags_off + 2 * static_cast<size_t>(world) * sizeof(unsigned int);
+  CU_TRY(cudaMalloc(reinterpret_cast<void**>(&X.local), X.bytes));
+  CU_TRY(cudaMalloc(reinterpret_cast<void**>(&X.stage), X.part_cap));
+  CU_TRY(cudaMalloc(reinterpret_cast<void**>(&X.counter), sizeof(int)));
+  CU_TRY(cudaMemset(X.local, 0, X.bytes));
+  CU_TRY(cudaMemset(X.counter, 0, sizeof(int)));
+  CU_TRY(cudaDeviceSynchronize());
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+  cudaIpcMemHandle_t h;
+  CU_TRY(cudaIpcGetMemHandle(&h, X.local));
+  std::memcpy(handle_out, &h, sizeof(h));
+  return B2F_OK;
+}
+
+int b2f_xchg_connect(b2f_index* idx, const void* handles) {
+  if (!idx || !handles || !idx->xchg.local) return fail(B2F_ERR_INVALID, "exchange not created");
+  auto& X = idx->xchg;
+  CU_TRY(cudaSetDevice(idx->shards[0].dev));
+  for (int r = 0; r < X.world; ++r) {
+    if (r == X.rank) { X.peer[r] = X.local; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char*>(handles) + 64 * r, sizeof(h));
+    void* p = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    X.peer[r] = static_cast<char*>(p);
+  }
+  X.connected = true;
+  return B2F_OK;
+}
+
+// push the staged local part to every rank and merge what every rank pushed (both asynchronous)
+static int xchg_push_and_merge(b2f_index* idx, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+  auto& X = idx->xchg;
+  Shard& S = idx->shards[0];
+  const unsigned int seq = ++X.seq;
+  const int par = static_cast<int>(seq & 1u);
+  XchgPeers peers;
+  peers.world = X.world;
+  for (int r = 0; r < X.world; ++r) {
+    peers.part[r] = X.peer[r] + (static_cast<size_t>(par) * X.world + X.rank) * X.part_cap;
+    peers.flag[r] = reinterpret_cast<unsigned int*>(X.peer[r] + X.flags_off) + par * X.world + X.rank;
+  }
+  const int64_t i_off = round_up(nq * k * 4, 16);
+  const int64_t n_vec = (i_off + nq * k * 8 + 15) / 16;
+  xchg_push_kernel<<<dim3(X.world, 4), 256, 0, S.stream>>>(reinterpret_cast<const uint4*>(X.stage), n_vec, peers, seq,
+                                                           X.counter);
+  CU_TRY(cudaGetLastError());
+  xchg_merge_kernel<<<static_cast<int>(nq), 256, 0, S.stream>>>(
+      X.local + static_cast<size_t>(par) * X.world * X.part_cap,
+      reinterpret_cast<const unsigned int*>(X.local + X.flags_off) + par * X.world, seq, X.world,
+      static_cast<int64_t>(X.part_cap), i_off, nq, k, D_dev, I_dev, idx->merge_flag_dev, idx->merge_flag_dev + 1);
+  CU_TRY(cudaGetLastError());
+  idx->stats.launches += 2;
+  return B2F_OK;
+}
+
+int b2f_search_xchg_async(b2f_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
+                          int repush_only) {
+  B2F_TRY(check_args_search(idx, q_dev, nq, k, D_dev, I_dev));
+  if (!idx->xchg.connected) return fail(B2F_ERR_INVALID, "exchange not connected (b2f_xchg_create / b2f_xchg_connect)");
+  if (nq > idx->xchg.max_nq || k > idx->xchg.max_k || nq * static_cast<int64_t>(k) > idx->xchg.max_nq * idx->xchg.max_k)
+    return fail(B2F_ERR_INVALID, "batch exceeds the exchange buffers");
+  if (nq == 0) return B2F_OK;
+  auto& X = idx->xchg;
+  float* Dl = reinterpret_cast<float*>(X.stage);
+  int64_t* Il = reinterpret_cast<int64_t*>(X.stage + round_up(nq * k * 4, 16));
+  if (!repush_only) B2F_TRY(b2f_search_device_async(idx, q_dev, nq, k, Dl, Il));
+  CU_TRY(cudaSetDevice(idx->shards[0].dev));
+  return xchg_push_and_merge(idx, nq, k, D_dev, I_dev);
+}
+
 int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_host, int64_t* I_host) {
   B2F_TRY(check_args_search(idx, q_host, nq, k, D_host, I_host));
   if (nq == 0) return B2F_OK;
@@ -1223,6 +1328,9 @@ int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
   else if (k == "score_launches") *out = s.score_launches;
   else if (k == "score_rows") *out = s.score_rows;
   else if (k == "select_ms") *out = s.select_ms;
+  else if (k == "xchg_timeout") {
+    *out = idx->merge_flag_host ? static_cast<double>(idx->merge_flag_host[1]) : 0.0;
+  }
   else if (k == "merge_saw_overflow") {   // read-and-clear; meaningful after the stream has been synchronised
     *out = idx->merge_flag_host ? static_cast<double>(*idx->merge_flag_host) : 0.0;
     if (idx->merge_flag_host) *idx->merge_flag_host = 0;

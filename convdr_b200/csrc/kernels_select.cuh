@@ -516,26 +516,23 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
 // other list, the number of elements that precede it; ties go to the earlier part, then the earlier
 // position (the reference's merge keeps the earlier block on `>=`, :218).
 // Part g starts at Dp + g*strideD floats / Ip + g*strideI int64s (nq*k for two dense arrays; the
-// packed [D | I] records gathered over NCCL use the packed part size).
-__global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ Dp,
-                                                    const int64_t* __restrict__ Ip, int G, int64_t nq,
-                                                    int k, float* __restrict__ D, int64_t* __restrict__ I,
-                                                    int64_t strideD, int64_t strideI,
-                                                    int* __restrict__ saw_overflow /* mapped host int or null */) {
-  const int64_t q = blockIdx.x;
-  __shared__ int total_valid;
-  if (threadIdx.x == 0) total_valid = 0;
+// packed [D | I] records of the exchange use the packed part size).  Parts are read with ld.global.cg:
+// in the peer-memory exchange they are written by OTHER GPUs while this kernel is already resident.
+__device__ __forceinline__ void merge_body(const float* Dp, const int64_t* Ip, int G, int64_t q,
+                                           int k, float* __restrict__ D, int64_t* __restrict__ I,
+                                           int64_t strideD, int64_t strideI, int* saw_overflow, int* total_valid_s) {
+  if (threadIdx.x == 0) *total_valid_s = 0;
   __syncthreads();
   const int E = G * k;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     const int g = e / k, i = e - g * k;
     const int64_t baseD = static_cast<int64_t>(g) * strideD + q * k;
     const int64_t baseI = static_cast<int64_t>(g) * strideI + q * k;
-    const int64_t id = Ip[baseI + i];
+    const int64_t id = __ldcg(Ip + baseI + i);
     if (id == -2 && saw_overflow != nullptr) *saw_overflow = 1;   // a shard's list overflowed: result pending its re-run
     if (id < 0) continue;
-    atomicAdd(&total_valid, 1);
-    const float s = Dp[baseD + i];
+    atomicAdd(total_valid_s, 1);
+    const float s = __ldcg(Dp + baseD + i);
     int rank = i;
     for (int g2 = 0; g2 < G; ++g2) {
       if (g2 == g) continue;
@@ -545,8 +542,8 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ Dp
       int lo = 0, hi = k;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const bool valid = Ip[b2I + mid] >= 0;
-        const float s2 = Dp[b2D + mid];
+        const bool valid = __ldcg(Ip + b2I + mid) >= 0;
+        const float s2 = __ldcg(Dp + b2D + mid);
         const bool before = valid && (s2 > s || (s2 == s && g2 < g));
         if (before) lo = mid + 1; else hi = mid;
       }
@@ -558,10 +555,84 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ Dp
     }
   }
   __syncthreads();
-  for (int i = total_valid + threadIdx.x; i < k; i += blockDim.x) {
+  for (int i = *total_valid_s + threadIdx.x; i < k; i += blockDim.x) {
     D[q * k + i] = -3.402823466e+38f;
     I[q * k + i] = -1;
   }
+}
+
+__global__ void __launch_bounds__(256) merge_kernel(const float* Dp, const int64_t* Ip, int G, int64_t nq,
+                                                    int k, float* __restrict__ D, int64_t* __restrict__ I,
+                                                    int64_t strideD, int64_t strideI,
+                                                    int* __restrict__ saw_overflow /* mapped host int or null */) {
+  __shared__ int total_valid;
+  merge_body(Dp, Ip, G, blockIdx.x, k, D, I, strideD, strideI, saw_overflow, &total_valid);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer-memory exchange of the one-process-per-GPU layout (replaces ncclAllGather + merge).
+//
+// Every rank owns an exchange buffer  [2 parities][world parts][part_cap bytes] + flags[2][world]
+// that all peers have mapped (CUDA IPC, NVLink).  Step `seq` (parity seq & 1):
+//   xchg_push_kernel : copies this rank's packed [D | I] part into slot `rank` of EVERY rank's buffer
+//                      with 16-byte stores over NVLink; the last block to finish publishes
+//                      flags[parity][rank] = seq on every rank (fence.sys + release store);
+//   xchg_merge_kernel: waits until the `world` flags of its own buffer reach seq (acquire loads),
+//                      then merges the parts exactly like merge_kernel.
+// No host round trip, no NCCL kernel, no proxy thread.  Reuse of a parity two steps later is safe:
+// a rank's merge of step s+1 cannot complete before every peer pushed step s+1, which each peer
+// enqueues after its own merge of step s.
+// ---------------------------------------------------------------------------------------------
+constexpr int kXchgMaxWorld = 16;
+struct XchgPeers {
+  char* part[kXchgMaxWorld];        // peer r: address of slot [parity][my rank] in r's buffer
+  unsigned int* flag[kXchgMaxWorld];  // peer r: address of flags[parity][my rank] in r's buffer
+  int world;
+};
+
+__global__ void __launch_bounds__(256) xchg_push_kernel(const uint4* __restrict__ stage, int64_t n_vec /* 16-byte units */,
+                                                        XchgPeers peers, unsigned int seq, int* __restrict__ counter) {
+  const int r = blockIdx.x;   // destination rank
+  uint4* dst = reinterpret_cast<uint4*>(peers.part[r]);
+  for (int64_t i = static_cast<int64_t>(blockIdx.y) * blockDim.x + threadIdx.x; i < n_vec;
+       i += static_cast<int64_t>(gridDim.y) * blockDim.x)
+    dst[i] = stage[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                                    // this block's stores, system-wide
+    const int total = static_cast<int>(gridDim.x * gridDim.y);
+    if (atomicAdd(counter, 1) == total - 1) {                  // last block of the launch
+      __threadfence_system();
+      *counter = 0;
+      for (int p = 0; p < peers.world; ++p)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.flag[p]), "r"(seq) : "memory");
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) xchg_merge_kernel(const char* __restrict__ parts /* [world][part_cap] of this parity */,
+                                                         const unsigned int* flags /* [world] of this parity */,
+                                                         unsigned int seq, int world, int64_t part_cap, int64_t i_off,
+                                                         int64_t nq, int k, float* __restrict__ D, int64_t* __restrict__ I,
+                                                         int* __restrict__ saw_overflow, int* __restrict__ err) {
+  __shared__ int total_valid;
+  if (threadIdx.x < world) {
+    long long t0 = 0;
+    for (unsigned int spin = 0;; ++spin) {
+      unsigned int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+      if (static_cast<int>(v - seq) >= 0) break;             // sequence numbers only grow (wrap-safe compare)
+      if ((spin & 255u) == 255u) {
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 8000000000ll) { if (err) *err = 1; break; }   // ~4 s: a peer died; report, never hang
+        __nanosleep(200);
+      }
+    }
+  }
+  __syncthreads();
+  merge_body(reinterpret_cast<const float*>(parts), reinterpret_cast<const int64_t*>(parts + i_off), world, blockIdx.x, k,
+             D, I, part_cap / 4, part_cap / 8, saw_overflow, &total_valid);
 }
 
 }  // namespace b2f

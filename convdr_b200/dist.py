@@ -61,6 +61,34 @@ class ShardedFlatIP:
         self.ntotal += n
         return lo, hi
 
+    # -- exchange --------------------------------------------------------------------------------
+    def enable_peer_exchange(self, max_nq: int, max_k: int) -> bool:
+        """Switch the result exchange from ncclAllGather + merge to the engine's own peer-memory
+        kernels (CUDA IPC over NVLink/NVSwitch; include/b2f.h b2f_xchg_*).  torch.distributed only
+        carries the 64-byte IPC handles, once.  Returns False (and keeps NCCL) if every rank cannot
+        map every other rank's buffer — the decision is collective."""
+        if self.world == 1 or self.index is None:
+            return False
+        ok, handle = 1, b"\0" * 64
+        try:
+            handle = self.index.xchg_create(self.rank, self.world, max_nq, max_k)
+        except RuntimeError:
+            ok = 0
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (ok, handle), group=self.group)
+        if all(g[0] for g in gathered):
+            try:
+                self.index.xchg_connect([g[1] for g in gathered])
+            except RuntimeError:
+                ok = 0
+        else:
+            ok = 0
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=self.group)
+        self._peer = all(flags)
+        self._peer_cap = (max_nq, max_k)
+        return self._peer
+
     # -- searching ------------------------------------------------------------------------------
     def _buffers(self, nq: int, k: int, device):
         """Packed exchange buffers: one part = [D float32 [nq,k] | pad to 16 B | I int64 [nq,k]]."""
@@ -105,6 +133,15 @@ class ShardedFlatIP:
         if self.world == 1:
             idx.search_device_async(q, k, D, I)
             return
+        if getattr(self, "_peer", False) and nq * k <= self._peer_cap[0] * self._peer_cap[1] and nq <= self._peer_cap[0] \
+                and k <= self._peer_cap[1]:
+            if getattr(self, "_ext", None) is None:
+                self._ext = torch.cuda.ExternalStream(idx.stream_ptr(0), device=q.device)
+            self._ext.wait_stream(torch.cuda.current_stream(q.device))
+            idx.search_xchg_async(q, k, D, I)     # search -> NVLink push -> wait + merge, all engine kernels
+            self._last_peer = True
+            return
+        self._last_peer = False
         send, recv = self._buffers(nq, k, q.device)
         if getattr(self, "_ext", None) is None:
             self._ext = torch.cuda.ExternalStream(idx.stream_ptr(0), device=q.device)
@@ -131,13 +168,19 @@ class ShardedFlatIP:
         if self.world == 1:
             idx.finish()
             return D, I
-        send, recv = self._send, self._recv
         # One host wait.  A local query whose candidate list overflowed (adversarial data) is re-run by
         # finish(); its rows travelled with the id -2 marker, which the merge kernel reports on EVERY
         # rank (they all merge the same gathered bytes), so the decision to repeat the exchange is
         # collective without an extra collective.
         idx.finish()
-        if idx.stat("merge_saw_overflow") > 0:
+        if idx.stat("xchg_timeout") > 0:
+            raise RuntimeError("peer exchange timed out: a rank's part never arrived")
+        redo = idx.stat("merge_saw_overflow") > 0      # read-and-clear; identical on every rank
+        if redo and self._last_peer:
+            idx.search_xchg_async(q, k, D, I, repush_only=True)
+            idx.finish()
+        elif redo:
+            send, recv = self._send, self._recv
             with torch.cuda.stream(self._ext):
                 dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)
                 idx.merge_packed_device_async(recv, self.world, self._part, self._i_off, nq, k, D, I)

@@ -169,6 +169,23 @@ class FlatIPIndex:
                                                              int(part_bytes), int(i_offset), int(nq), int(k),
                                                              D.data_ptr(), I.data_ptr()))
 
+    # -- peer-memory exchange (one process per GPU) ------------------------------------------------
+    def xchg_create(self, rank: int, world: int, max_nq: int, max_k: int) -> bytes:
+        """Allocate this rank's exchange buffer; returns its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        _lib.check(_lib.load().b2f_xchg_create(self._ensure(), int(rank), int(world), int(max_nq), int(max_k), buf))
+        return buf.raw
+
+    def xchg_connect(self, handles) -> None:
+        """handles: the 64-byte handles of all ranks, in rank order."""
+        blob = b"".join(handles)
+        _lib.check(_lib.load().b2f_xchg_connect(self._ensure(), blob))
+
+    def search_xchg_async(self, q, k: int, D, I, repush_only: bool = False) -> None:
+        """Collective: local search -> NVLink push of the packed part to every rank -> wait + merge."""
+        _lib.check(_lib.load().b2f_search_xchg_async(self._ensure(), q.data_ptr(), q.shape[0], int(k), D.data_ptr(),
+                                                     I.data_ptr(), 1 if repush_only else 0))
+
     def reset_stats(self) -> None:
         self.set_option("reset_stats", 1)
 

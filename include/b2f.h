@@ -129,6 +129,27 @@ int b2f_merge_packed_device_async(b2f_index* idx, const void* parts_dev, int n_p
                                   int64_t part_bytes, int64_t i_offset_bytes, int64_t nq, int k,
                                   float* D_dev, int64_t* I_dev);
 
+/* Peer-memory exchange for the one-process-per-GPU layout (one single-shard index
+ * per rank, all ranks on one NVLink/NVSwitch node): replaces ncclAllGather +
+ * merge by two kernels that talk through CUDA-IPC-mapped buffers.
+ *   b2f_xchg_create   allocates this rank's exchange buffer for batches up to
+ *                     max_nq x max_k and returns its 64-byte cudaIpcMemHandle_t;
+ *   b2f_xchg_connect  takes the world x 64 bytes of handles of ALL ranks (rank
+ *                     order; exchanged by the caller, e.g. torch.distributed);
+ *   b2f_search_xchg_async  local search (ids must be global: add_with_ids /
+ *                     add_synthetic) -> push of the packed [nq,k] part into every
+ *                     rank's buffer over NVLink -> wait for all ranks' parts ->
+ *                     merge into D_dev / I_dev; all enqueued, settle with
+ *                     b2f_search_finish.  Collective: every rank must call it with
+ *                     the same nq, k.  repush_only != 0 skips the local search
+ *                     (used after finish() re-ran overflowed queries; stat
+ *                     "merge_saw_overflow" tells every rank when that is needed).
+ * Stat "xchg_timeout" is 1 if a rank's part never arrived (~4 s).               */
+int b2f_xchg_create(b2f_index* idx, int rank, int world, int64_t max_nq, int max_k, void* handle_out);
+int b2f_xchg_connect(b2f_index* idx, const void* handles);
+int b2f_search_xchg_async(b2f_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
+                          int64_t* I_dev, int repush_only);
+
 /* faiss IndexFlat.reconstruct_n(i0, ni): copy stored rows [row0, row0+n) of shard
  * `shard` (shard-local positions) back to host memory — inspection / tests.    */
 int b2f_reconstruct_n(b2f_index* idx, int shard, int64_t row0, int64_t n, float* out_host);

@@ -1,0 +1,71 @@
+"""Worker of tests/test_gpu_parity.py::test_peer_memory_exchange_equals_nccl_exchange (2+ GPUs):
+one process per GPU; the same sharded searches through ncclAllGather + merge and through the engine's
+peer-memory exchange kernels must give bit-identical results, equal to a single index over everything."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from convdr_b200 import FlatIPIndex, synth
+from convdr_b200.dist import ShardedFlatIP
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", init_method="env://", device_id=dev)
+    n = 60000
+    P = synth.block(0, n, seed=41)
+    P[50000:51500] = P[50000]                       # 1500 identical rows (> the survivor capacity): overflow on the owning rank
+    idx = FlatIPIndex(768, devices=[dev.index])
+    sh = ShardedFlatIP(index=idx)
+    sh.add(P)
+    full = FlatIPIndex(768, devices=[dev.index])
+    full.add(P)
+    results = {}
+    for mode in ("nccl", "peer"):
+        if mode == "peer":
+            assert sh.enable_peer_exchange(400, 1000)
+        out = []
+        for nq, k, seed in ((1, 10, 1), (37, 100, 2), (173, 100, 3), (300, 64, 4), (8, 1000, 5)):
+            q = torch.from_numpy(synth.block(0, nq, seed=seed, stream=1)).to(dev)
+            D, I = sh.search(q, k)
+            out.append((D.cpu().numpy(), I.cpu().numpy()))
+            Df, If = full.search(q.cpu().numpy(), k)
+            np.testing.assert_array_equal(out[-1][1], If)
+            np.testing.assert_array_equal(out[-1][0], Df)
+        # a query equal to the duplicated row: every duplicate ties, the owning rank's list overflows,
+        # the marker travels, every rank repeats the exchange after the local re-run
+        q = torch.from_numpy(np.ascontiguousarray(P[50000:50008])).to(dev)   # 8 queries: tensor engine
+        idx.reset_stats()
+        D, I = sh.search(q, 50)
+        assert idx.stat("fallback_queries") == (8 if rank == world - 1 else 0)
+        Df, If = full.search(q.cpu().numpy(), 50)
+        np.testing.assert_array_equal(I.cpu().numpy(), If)
+        np.testing.assert_array_equal(D.cpu().numpy(), Df)
+        out.append((D.cpu().numpy(), I.cpu().numpy()))
+        # queued searches, one settle
+        q = torch.from_numpy(synth.block(0, 50, seed=9, stream=1)).to(dev)
+        outs = [(torch.empty((50, 20), dtype=torch.float32, device=dev), torch.empty((50, 20), dtype=torch.int64, device=dev))
+                for _ in range(6)]
+        for D, I in outs:
+            sh.search_async(q, 20, D, I)
+        assert sh.finish()
+        Df, If = full.search(q.cpu().numpy(), 20)
+        for D, I in outs:
+            np.testing.assert_array_equal(I.cpu().numpy(), If)
+            np.testing.assert_array_equal(D.cpu().numpy(), Df)
+        results[mode] = out
+    for (Da, Ia), (Db, Ib) in zip(results["nccl"], results["peer"]):
+        np.testing.assert_array_equal(Ia, Ib)
+        np.testing.assert_array_equal(Da, Db)
+    dist.barrier()
+    if rank == 0:
+        print("XCHG_OK", world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -427,3 +427,17 @@ def test_search_resident_over_flat_shards_matches_block_loop(tmp_path):
     score_of = lambda qi, ids: Q[qi].astype(np.float64) @ P[ids].astype(np.float64).T
     r = flat_ip.compare(Dr.astype(np.float32), Ir, Do[:, :40].astype(np.float32), Io[:, :40], score_of, rtol=RTOL)
     assert r["violations"] == 0, r
+
+
+def test_peer_memory_exchange_equals_nccl_exchange(gpu_count):
+    """One process per GPU (torchrun, NCCL rendezvous on 127.0.0.1): the peer-memory exchange kernels and
+    the ncclAllGather path agree bit for bit with a single index, including the overflow re-run."""
+    import subprocess
+    import sys
+    if gpu_count < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "_xchg_worker.py")]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "XCHG_OK 2" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
