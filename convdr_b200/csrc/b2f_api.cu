@@ -619,7 +619,14 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       ++phase;
       break;
     }
-    {
+    if (tensor && idx->tighten && phase == 0) {   // TS bootstrap: select in shared memory + histogram seed
+      ProfScope ps(idx, S, 1);
+      int P = 4096;
+      while (P < plan.n0 + plan.S && P < 16384) P <<= 1;   // longer lists are gathered to global memory
+      bootstrap_select_kernel<<<nqp, kFinThreads, static_cast<size_t>(P) * sizeof(uint64_t), s>>>(
+          W.cand[cur], W.cand[cur ^ 1], W.gath, W.cnt, C, k, W.margin, W.tau, plan.S, plan.cap_p, S.max_pairs, W.cnt2,
+          W.ovf, W.hist, W.hkey0, W.hshift, P);
+    } else {
       ProfScope ps(idx, S, 1);
       refresh_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.gath, W.cnt, C, k, plan.exact ? 1 : 0,
                                                 W.margin, W.tau, W.tauP, n_override, plan.S, plan.cap_p,
@@ -703,6 +710,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
       CU_TRY(cudaFuncSetAttribute(umma_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmemBytes));
       CU_TRY(cudaFuncSetAttribute(umma_ss_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemLimit));
       CU_TRY(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 8));
+      CU_TRY(cudaFuncSetAttribute(bootstrap_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
       attr_set[S.dev & 63] = true;
     }
   } else {

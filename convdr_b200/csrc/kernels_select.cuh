@@ -360,34 +360,44 @@ __device__ __forceinline__ unsigned int fin_scan256(unsigned int v, FinSmem& sm)
   return v + base;
 }
 
-__global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
-    const uint64_t* __restrict__ cand, uint64_t* __restrict__ gath, const int* __restrict__ cnt, int C, int k,
-    const float* __restrict__ margin, int S, int cap_p, int max_pairs, const int* __restrict__ cnt2,
-    const int* __restrict__ ovf, int* __restrict__ ovf_out, const float* __restrict__ q32,
-    const float* __restrict__ x32, const Seg* __restrict__ segs, int nseg, const int64_t* __restrict__ idmap,
-    float* __restrict__ D_out, int64_t* __restrict__ I_out, int64_t out_stride, int P) {
-  extern __shared__ __align__(16) uint64_t fin_buf[];   // [2][P]
-  __shared__ FinSmem sm;
-  __shared__ __align__(16) float Qs[kD];
-  const int q = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t* list = cand + static_cast<int64_t>(q) * C;
-  uint64_t* bufA = fin_buf;
-  uint64_t* bufB = fin_buf + P;
-  for (int i = tid; i < kD; i += kFinThreads) Qs[i] = q32[static_cast<int64_t>(q) * kD + i];
+// Front part shared by bootstrap_select_kernel and finalize_kernel (all kFinThreads threads call it):
+// gather the segmented list of query q (survivors [0,m) + one private area per CTA pair) into `bufA`
+// (shared memory, P records; longer lists go to `gath_q` in global memory), radix-select the key of
+// the k-th best approximate score, derive the survivor threshold T = fkey(kth - margin) << 32.
+struct FinFront {
+  uint64_t* in;        // gathered list
+  int n;               // its length
+  int nvalid;          // non-empty records in it
+  uint32_t kth_key;    // key of the k-th best approximate score (0xffffffff: fewer than k records)
+  float tau;           // kth - margin (rounded down), -inf if fewer than k records
+  uint64_t T;          // record threshold of tau (0: keep everything)
+};
 
+// histogram update with the increments of one warp pre-combined per bucket: in the first radix passes
+// nearly all keys share their digit, and 32 same-address shared-memory atomics serialise
+__device__ __forceinline__ void hist_add_aggregated(unsigned int* hist, bool active, unsigned int digit) {
+  const unsigned int d = active ? digit : 0xffffffffu;
+  const unsigned int peers = __match_any_sync(0xffffffffu, d);
+  if (active && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], static_cast<unsigned int>(__popc(peers)));
+}
+
+__device__ __forceinline__ FinFront fin_front(const uint64_t* __restrict__ list, uint64_t* __restrict__ gath_q, int m,
+                                              int S, int cap_p, int max_pairs, const int* __restrict__ cnt2q, int k,
+                                              float margin_q, uint64_t* bufA, int P, FinSmem& sm) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  FinFront f;
   // ---- 1. segment offsets ----
-  const int m = min(cnt[q], S);
   {
     unsigned int c = 0;
-    if (tid < max_pairs) c = static_cast<unsigned int>(min(cnt2[q * max_pairs + tid], cap_p));
+    if (tid < max_pairs) c = static_cast<unsigned int>(min(cnt2q[tid], cap_p));
     const unsigned int inc = fin_scan256(tid < 256 ? c : 0u, sm);
     if (tid < max_pairs) sm.seg_off[tid] = static_cast<int>(inc - c);
     if (tid == max_pairs - 1) sm.seg_off[max_pairs] = static_cast<int>(inc);
+    if (max_pairs == 0 && tid == 0) sm.seg_off[0] = 0;
     __syncthreads();
   }
   const int n = m + sm.seg_off[max_pairs];
-  uint64_t* in = (n <= P) ? bufA : gath + static_cast<int64_t>(q) * C;
+  uint64_t* in = (n <= P) ? bufA : gath_q;
 
   // ---- 2. gather ----
   for (int i = tid; i < m; i += kFinThreads) in[i] = list[i];
@@ -408,18 +418,23 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
     if (lane == 0 && c) atomicAdd(&sm.nvalid, c);
     __syncthreads();
   }
-  const int nvalid = static_cast<int>(sm.nvalid);
-  uint64_t T = 0ull;
-  if (nvalid >= k) {
+  f.in = in;
+  f.n = n;
+  f.nvalid = static_cast<int>(sm.nvalid);
+  f.kth_key = 0xffffffffu;
+  f.tau = -INFINITY;
+  f.T = 0ull;
+  if (f.nvalid >= k) {
     uint32_t prefix = 0, mask = 0;
     unsigned int remaining = static_cast<unsigned int>(k);
     for (int pass = 0; pass < 4; ++pass) {
       const int shift = 24 - 8 * pass;
       if (tid < 256) sm.hist[tid] = 0;
       __syncthreads();
-      for (int i = tid; i < n; i += kFinThreads) {
-        const uint32_t key = static_cast<uint32_t>(in[i] >> 32);
-        if (key != 0u && (key & mask) == prefix) atomicAdd(&sm.hist[(key >> shift) & 255u], 1u);
+      for (int i0 = 0; i0 < n; i0 += kFinThreads) {
+        const int i = i0 + tid;
+        const uint32_t key = (i < n) ? static_cast<uint32_t>(in[i] >> 32) : 0u;
+        hist_add_aggregated(sm.hist, key != 0u && (key & mask) == prefix, (key >> shift) & 255u);
       }
       __syncthreads();
       const unsigned int h = (tid < 256) ? sm.hist[255 - tid] : 0u;   // thread t owns bucket 255-t (descending)
@@ -434,9 +449,99 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
       remaining = sm.remaining;
       __syncthreads();
     }
-    const float t = __fsub_rd(key2f(prefix), margin[q]);
-    T = static_cast<uint64_t>(fkey(t)) << 32;
+    f.kth_key = prefix;
+    f.tau = __fsub_rd(key2f(prefix), margin_q);
+    f.T = static_cast<uint64_t>(fkey(f.tau)) << 32;
   }
+  return f;
+}
+
+// Bootstrap step of a tensor-engine (TS) pass, one 512-thread block per query, after the dense launch:
+// select the k-th best approximate score of the first n0 rows (list held in shared memory), publish
+// tau, keep the survivors (records >= tau) in [0, S) of `cand_out`, seed the tightening histogram of
+// the main launch (kernels_umma.cuh, refresher role) and clear the per-pair counters.
+__global__ void __launch_bounds__(kFinThreads, 2) bootstrap_select_kernel(
+    const uint64_t* __restrict__ cand_in, uint64_t* __restrict__ cand_out, uint64_t* __restrict__ gath,
+    int* __restrict__ cnt, int C, int k, const float* __restrict__ margin, float* __restrict__ tau, int S, int cap_p,
+    int max_pairs, int* __restrict__ cnt2, int* __restrict__ ovf, unsigned int* __restrict__ hist,
+    uint32_t* __restrict__ hkey0, int* __restrict__ hshift, int P) {
+  extern __shared__ __align__(16) uint64_t fin_buf[];   // [P]
+  __shared__ FinSmem sm;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const FinFront f = fin_front(cand_in + static_cast<int64_t>(q) * C, gath + static_cast<int64_t>(q) * C, min(cnt[q], S), S,
+                               cap_p, max_pairs, cnt2 + q * max_pairs, k, margin[q], fin_buf, P, sm);
+  uint64_t* out = cand_out + static_cast<int64_t>(q) * C;
+  // survivors -> [0, S) of the other list
+  for (int i0 = 0; i0 < f.n; i0 += kFinThreads) {
+    const int i = i0 + tid;
+    const uint64_t rec = (i < f.n) ? f.in[i] : 0ull;
+    const bool keep = rec != 0ull && rec >= f.T;
+    const unsigned int b = __ballot_sync(0xffffffffu, keep);
+    if (b) {
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(&sm.count, __popc(b));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const unsigned int pos = base + __popc(b & ((1u << lane) - 1u));
+      if (keep && pos < static_cast<unsigned int>(S)) out[pos] = rec;
+    }
+  }
+  // histogram seed: buckets of 2^shift keys from the k-th key, kTightenBuckets of them spanning 4x the
+  // distance to the best key seen (see refresh_kernel)
+  uint32_t kmax = 0;
+  for (int i = tid; i < f.n; i += kFinThreads) kmax = max(kmax, static_cast<uint32_t>(f.in[i] >> 32));
+#pragma unroll
+  for (int s2 = 16; s2 >= 1; s2 >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, s2));
+  if (tid == 0) sm.digit = 0;
+  if (tid < kTightenBuckets) sm.hist[tid] = 0;
+  __syncthreads();
+  if (lane == 0) atomicMax(&sm.digit, kmax);
+  __syncthreads();
+  kmax = sm.digit;
+  const uint32_t key0 = f.kth_key;
+  int shift = 0;
+  if (key0 != 0xffffffffu) {
+    const uint64_t span = 4ull * static_cast<uint64_t>(kmax - key0) + 1ull;
+    while ((static_cast<uint64_t>(kTightenBuckets) << shift) < span) ++shift;
+    for (int i0 = 0; i0 < f.n; i0 += kFinThreads) {
+      const int i = i0 + tid;
+      const uint64_t rec = (i < f.n) ? f.in[i] : 0ull;
+      const uint32_t key = static_cast<uint32_t>(rec >> 32);
+      const bool on = rec != 0ull && key >= key0;
+      hist_add_aggregated(sm.hist, on, on ? min(static_cast<uint32_t>(kTightenBuckets - 1), (key - key0) >> shift) : 0u);
+    }
+  }
+  __syncthreads();
+  if (tid < kTightenBuckets) hist[static_cast<int64_t>(q) * kTightenBuckets + tid] = sm.hist[tid];
+  for (int p = tid; p < max_pairs; p += kFinThreads) cnt2[q * max_pairs + p] = 0;
+  if (tid == 0) {
+    const int msurv = static_cast<int>(sm.count);
+    cnt[q] = min(msurv, S);
+    tau[q] = f.tau;
+    hkey0[q] = key0;
+    hshift[q] = shift;
+    if (msurv > S) ovf[q] = 1;   // more rows within the error margin of the k-th score than the list holds
+  }
+}
+
+__global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
+    const uint64_t* __restrict__ cand, uint64_t* __restrict__ gath, const int* __restrict__ cnt, int C, int k,
+    const float* __restrict__ margin, int S, int cap_p, int max_pairs, const int* __restrict__ cnt2,
+    const int* __restrict__ ovf, int* __restrict__ ovf_out, const float* __restrict__ q32,
+    const float* __restrict__ x32, const Seg* __restrict__ segs, int nseg, const int64_t* __restrict__ idmap,
+    float* __restrict__ D_out, int64_t* __restrict__ I_out, int64_t out_stride, int P) {
+  extern __shared__ __align__(16) uint64_t fin_buf[];   // [2][P]
+  __shared__ FinSmem sm;
+  __shared__ __align__(16) float Qs[kD];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t* bufB = fin_buf + P;
+  for (int i = tid; i < kD; i += kFinThreads) Qs[i] = q32[static_cast<int64_t>(q) * kD + i];
+  const FinFront f = fin_front(cand + static_cast<int64_t>(q) * C, gath + static_cast<int64_t>(q) * C, min(cnt[q], S), S, cap_p,
+                               max_pairs, cnt2 + q * max_pairs, k, margin[q], fin_buf, P, sm);
+  const uint64_t* in = f.in;
+  const int n = f.n;
+  const uint64_t T = f.T;
 
   // ---- 4. survivors: every record within the margin of the k-th score ----
   for (int i0 = 0; i0 < n; i0 += kFinThreads) {
