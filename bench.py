@@ -64,15 +64,17 @@ def parse_args():
 
 
 def measured_peaks():
+    """(HBM GB/s, bf16 TFLOP/s sustained, source).  MEASURED_PEAKS.json is driver-written per pod."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
             with open(path) as f:
                 j = json.load(f)
-            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained") or j.get("bf16_tflops") or 0.0), \
+                "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1500.0, "fallback (B200_PROFILING.md)"
 
 
 def ncu_traffic_per_launch(rows_per_launch: float):
@@ -399,7 +401,7 @@ def run_b2f_arm(args):
     else:
         stats_sum = stats_local
     if rank == 0:
-        peak, peak_src = measured_peaks()
+        peak, tensor_peak, peak_src = measured_peaks()
         sl = stats_local.tolist()
         # dominant kernel: umma_score_select_kernel.  Per launch: rows streamed * 1536 B (bf16 shadow).
         ms_per_launch = sl[0] / max(sl[1], 1.0)
@@ -429,6 +431,14 @@ def run_b2f_arm(args):
                 "score_kernel_share_of_step": sl[0] / dev_ms_max if dev_ms_max else None,
                 "select_kernels_ms_per_step": sl[4] / args.steps,
                 "whole_step_streamed_gbs_per_gpu": n_local * BYTES_STREAMED_PER_ROW * args.steps / (dev_ms_max * 1e-3) / 1e9,
+                # the same kernel against the tensor roofline: a pass issues M = 256 query lanes per row
+                # whatever nq is (tcgen05 cta_group::2 M granularity), so 173 queries pay for 256
+                "tensor": (lambda rps, passes: {
+                    "issued_tflops": rps * 2 * 256 * D / 1e12,
+                    "useful_tflops": rps * 2 * (nq / passes) * D / 1e12,
+                    "peak_bf16_sustained_tflops": tensor_peak,
+                    "frac_issued": (rps * 2 * 256 * D / 1e12) / tensor_peak if tensor_peak else None,
+                })(rows_per_launch / (ms_per_launch * 1e-3) if ms_per_launch > 0 else 0.0, max(-(-nq // 256), 1)),
             },
             "e2e": {"value": nq * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(q_host.nbytes) * n_gpus,

@@ -212,6 +212,8 @@ struct b2f_index {
   int umma_variant = 0;   // 0 auto, 1 smem-stationary queries (SS), 2 TMEM-stationary queries (TS)
   int l2_prefetch = 1;
   int worst_case_margin = 0;  // 1: bf16 margin from the data-independent worst case (A/B only)
+  int bootstrap = 0;      // TS engine with tightening: 1 = dense bootstrap launch + bootstrap_select_kernel before the
+                          // main launch, 0 = none (thresholds start at -inf inside the single launch)
   int tighten = 400;      // TS engine: in-kernel threshold tightening through a global hit histogram (one
                           // launch after the bootstrap); pause of the refresher between rounds in ns,
                           // 0 = off (geometric phases with a refresh kernel between them).
@@ -391,8 +393,22 @@ int ensure_pin(Shard& S, size_t bytes) {
 __global__ void pass_init_kernel(const float* __restrict__ qnorm, const float* __restrict__ qerr,
                                  const unsigned int* __restrict__ maxnorm2_bits, int mode, float scale, float u_scan,
                                  float* __restrict__ margin, int* __restrict__ cnt,
-                                 int* __restrict__ ovf, int* __restrict__ cnt2, int max_pairs) {
+                                 int* __restrict__ ovf, int* __restrict__ cnt2, int max_pairs,
+                                 unsigned int* __restrict__ hist, uint32_t* __restrict__ hkey0, int* __restrict__ hshift,
+                                 float* __restrict__ tau) {
   const int q = blockIdx.x;
+  if (hist != nullptr) {
+    // TS engine without a bootstrap launch: empty tightening histogram of 64 buckets per binade over
+    // the eight binades below R = (1 + 2^-6) * ||q|| * max||p|| >= |any prefilter score of q|; tau = -inf.
+    for (int b = threadIdx.x; b < kHistBuckets; b += blockDim.x) hist[static_cast<int64_t>(q) * kHistBuckets + b] = 0u;
+    if (threadIdx.x == 0) {
+      const float R = __fmul_ru(__fmul_ru(qnorm[q], __fsqrt_ru(__uint_as_float(maxnorm2_bits[0]))), 1.015625f);
+      const uint32_t top = fkey(R) >> 17;
+      hkey0[q] = (top >= static_cast<uint32_t>(kHistBuckets - 1) ? top - (kHistBuckets - 1) : 0u) << 17;
+      hshift[q] = 17;
+      tau[q] = -INFINITY;
+    }
+  }
   if (threadIdx.x == 0) {
     const float P = __fsqrt_ru(__uint_as_float(maxnorm2_bits[0]));
     float eps = 0.f;
@@ -520,6 +536,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   cudaStream_t s = S.stream;
   const bool tensor = plan.path == B2F_PATH_UMMA_BF16 && plan.variant == 2;   // TS: segmented lists
   const bool tensor_ss = plan.path == B2F_PATH_UMMA_BF16 && plan.variant == 1;
+  const bool one_launch = tensor && idx->tighten && !idx->bootstrap;   // no bootstrap: ONE scoring launch per pass
   if (tensor) {
     if (!W.areas_clean) {   // only after (re)allocation or after another engine used the lists
       CU_TRY(cudaMemsetAsync(W.cand[0], 0, sizeof(uint64_t) * static_cast<size_t>(W.qp_cap) * W.C, s));
@@ -532,7 +549,8 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   const int margin_mode = plan.exact ? 0 : (plan.path == B2F_PATH_UMMA_BF16 ? (idx->worst_case_margin ? 3 : 2) : 1);
   pass_init_kernel<<<nqp, 128, 0, s>>>(qnormp, qerrp, S.maxnorm2, margin_mode,
                                        static_cast<float>(idx->margin_ppm * 1e-6 * 1.0000001), static_cast<float>(kUScan),
-                                       W.margin, W.cnt, W.ovf, tensor ? W.cnt2 : nullptr, S.max_pairs);
+                                       W.margin, W.cnt, W.ovf, tensor ? W.cnt2 : nullptr, S.max_pairs,
+                                       one_launch ? W.hist : nullptr, W.hkey0, W.hshift, W.tau);
   st.launches += 1;
 
   int cur = 0;
@@ -559,8 +577,9 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   int phase = 0;
   while (begin < N) {
     int64_t end;
-    const bool dense = (phase == 0);
-    if (dense) end = std::min<int64_t>(N, plan.n0);
+    const bool dense = (phase == 0) && !one_launch;
+    if (one_launch) end = N;
+    else if (dense) end = std::min<int64_t>(N, plan.n0);
     else if (plan.exact) end = std::min<int64_t>(N, begin + (C - k));
     else if (tensor && idx->tighten) end = N;   // thresholds are tightened inside the kernel
     else end = std::min<int64_t>(N, begin * std::max(2, idx->growth));
@@ -642,11 +661,14 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   }
   if (tensor) {
     ProfScope ps(idx, S, 1);
-    int P = 4096;
-    while (P < plan.S) P <<= 1;
-    finalize_kernel<<<nqp, kFinThreads, static_cast<size_t>(2) * P * sizeof(uint64_t), s>>>(
+    int PS = 1024;                       // survivors (bufB): >= S
+    while (PS < plan.S) PS <<= 1;
+    int P = 8192;                        // gathered list (bufA); longer lists go through global memory
+    while (P < PS) P <<= 1;
+    finalize_kernel<<<nqp, kFinThreads, static_cast<size_t>(P + PS) * sizeof(uint64_t), s>>>(
         W.cand[cur], W.gath, W.cnt, C, k, W.margin, plan.S, plan.cap_p, S.max_pairs, W.cnt2, W.ovf, ovf_dst, q32p,
-        S.x32, S.segs_d, static_cast<int>(S.segs.size()), S.has_ids ? S.idmap : nullptr, D_out, I_out, out_stride, P);
+        S.x32, S.segs_d, static_cast<int>(S.segs.size()), S.has_ids ? S.idmap : nullptr, D_out, I_out, out_stride, P,
+        idx->tighten ? W.tau : nullptr);
     CU_TRY(cudaGetLastError());
     st.launches += 1;
     st.passes += 1;
@@ -709,7 +731,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
     if (!attr_set[S.dev & 63]) {
       CU_TRY(cudaFuncSetAttribute(umma_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmemBytes));
       CU_TRY(cudaFuncSetAttribute(umma_ss_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemLimit));
-      CU_TRY(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 8));
+      CU_TRY(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 8));   // P + PS records
       CU_TRY(cudaFuncSetAttribute(bootstrap_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
       attr_set[S.dev & 63] = true;
     }
@@ -1309,6 +1331,8 @@ int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
   } else if (k == "tighten") {
     if (value < 0 || value > 1000000) return fail(B2F_ERR_INVALID, "tighten must be 0 (off) or a pause in ns <= 1e6");
     idx->tighten = static_cast<int>(value);
+  } else if (k == "bootstrap") {
+    idx->bootstrap = value ? 1 : 0;
   } else if (k == "worst_case_margin") {
     idx->worst_case_margin = value ? 1 : 0;
   } else if (k == "profile") {

@@ -12,14 +12,14 @@ namespace b2f {
 
 constexpr int kSelThreads = 256;
 constexpr int kSortCap = 2048;  // == B2F_MAX_K
-constexpr int kTightenBuckets = 128;  // == kHistBuckets of kernels_umma.cuh
+constexpr int kTightenBuckets = 512;  // == kHistBuckets of kernels_umma.cuh
 
 struct Seg {  // rows [local_start, local_start+count) of a shard carry ids global_start + i
   int64_t local_start, count, global_start;
 };
 
 struct SelectSmem {
-  unsigned int hist[256];
+  unsigned int hist[512];   // 256 radix buckets; 512 when seeding the tightening histogram
   unsigned int warp_tot[kSelThreads / 32];
   unsigned int digit, remaining, count, nvalid;
 };
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kSelThreads) refresh_kernel(
       const uint64_t span = 4ull * static_cast<uint64_t>(kmax - key0) + 1ull;
       while ((static_cast<uint64_t>(kTightenBuckets) << shift) < span) ++shift;
     }
-    if (threadIdx.x < kTightenBuckets) sm.hist[threadIdx.x] = 0;
+    for (int b = threadIdx.x; b < kTightenBuckets; b += kSelThreads) sm.hist[b] = 0;
     __syncthreads();
     if (key0 != 0xffffffffu) {
       for (int i = threadIdx.x; i < n; i += kSelThreads) {
@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(kSelThreads) refresh_kernel(
       }
     }
     __syncthreads();
-    if (threadIdx.x < kTightenBuckets) hist[static_cast<int64_t>(q) * kTightenBuckets + threadIdx.x] = sm.hist[threadIdx.x];
+    for (int b = threadIdx.x; b < kTightenBuckets; b += kSelThreads)
+      hist[static_cast<int64_t>(q) * kTightenBuckets + b] = sm.hist[b];
     if (threadIdx.x == 0) { hkey0[q] = key0; hshift[q] = shift; }
   }
 }
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kSelThreads) final_kernel(
 constexpr int kFinThreads = 512;   // two blocks per SM: 173 queries fit one wave on 148 SMs
 
 struct FinSmem {
-  unsigned int hist[256];
+  unsigned int hist[512];   // 256 radix buckets; 512 when seeding the tightening histogram
   unsigned int warp_tot[kFinThreads / 32];
   unsigned int digit, remaining, count, nvalid;
   int seg_off[129];
@@ -383,41 +384,56 @@ __device__ __forceinline__ void hist_add_aggregated(unsigned int* hist, bool act
 
 __device__ __forceinline__ FinFront fin_front(const uint64_t* __restrict__ list, uint64_t* __restrict__ gath_q, int m,
                                               int S, int cap_p, int max_pairs, const int* __restrict__ cnt2q, int k,
-                                              float margin_q, uint64_t* bufA, int P, FinSmem& sm) {
+                                              float margin_q, uint64_t Tlow, uint64_t* bufA, int P, FinSmem& sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   FinFront f;
-  // ---- 1. segment offsets ----
+  // ---- 1. upper bound of the list length decides where it is gathered ----
+  if (tid == 0) { sm.nvalid = 0; sm.count = 0; }
+  __syncthreads();
   {
-    unsigned int c = 0;
-    if (tid < max_pairs) c = static_cast<unsigned int>(min(cnt2q[tid], cap_p));
-    const unsigned int inc = fin_scan256(tid < 256 ? c : 0u, sm);
-    if (tid < max_pairs) sm.seg_off[tid] = static_cast<int>(inc - c);
-    if (tid == max_pairs - 1) sm.seg_off[max_pairs] = static_cast<int>(inc);
-    if (max_pairs == 0 && tid == 0) sm.seg_off[0] = 0;
+    int c = 0;
+    if (tid < max_pairs) c = min(cnt2q[tid], cap_p);
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+    if (lane == 0 && c) atomicAdd(&sm.nvalid, static_cast<unsigned int>(c));
     __syncthreads();
   }
-  const int n = m + sm.seg_off[max_pairs];
-  uint64_t* in = (n <= P) ? bufA : gath_q;
+  const int upper = m + static_cast<int>(sm.nvalid);
+  uint64_t* in = (upper <= P) ? bufA : gath_q;
 
-  // ---- 2. gather ----
-  for (int i = tid; i < m; i += kFinThreads) in[i] = list[i];
-  for (int p = warp; p < max_pairs; p += kFinThreads / 32) {
-    const int off = sm.seg_off[p], c = sm.seg_off[p + 1] - off;
-    const uint64_t* src = list + S + static_cast<int64_t>(p) * cap_p;
-    for (int e = lane; e < c; e += 32) in[m + off + e] = src[e];
+  // ---- 2. gather + filter: keep the non-empty records >= Tlow.  Tlow is any lower bound of the final
+  // survivor threshold (the last tau the in-kernel refresher published; 0 = keep all): everything at or
+  // above the k-th score minus the margin passes it, so neither the k-th score nor the survivor set
+  // changes, but the bulk of the early, loosely filtered appends never enters the select. ----
+  auto append = [&](uint64_t rec) {
+    const bool keep = rec != 0ull && rec >= Tlow;
+    const unsigned int b = __ballot_sync(0xffffffffu, keep);
+    if (b) {
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(&sm.count, __popc(b));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (keep) in[base + __popc(b & ((1u << lane) - 1u))] = rec;
+    }
+  };
+  for (int i0 = 0; i0 < m; i0 += kFinThreads) {
+    const int i = i0 + tid;
+    append(i < m ? list[i] : 0ull);
   }
-  if (tid == 0) { sm.nvalid = 0; sm.count = 0; }
+  for (int p = warp; p < max_pairs; p += kFinThreads / 32) {
+    const int c = min(cnt2q[p], cap_p);
+    const uint64_t* src = list + S + static_cast<int64_t>(p) * cap_p;
+    for (int e0 = 0; e0 < c; e0 += 32) {
+      const int e = e0 + lane;
+      append(e < c ? src[e] : 0ull);
+    }
+  }
+  __syncthreads();
+  const int n = static_cast<int>(sm.count);
+  __syncthreads();
+  if (tid == 0) { sm.nvalid = static_cast<unsigned int>(n); sm.count = 0; }
   __syncthreads();
 
   // ---- 3. k-th best approximate score (radix select on the 32-bit score key) ----
-  {
-    unsigned int c = 0;
-    for (int i = tid; i < n; i += kFinThreads) c += (in[i] != 0ull);
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
-    if (lane == 0 && c) atomicAdd(&sm.nvalid, c);
-    __syncthreads();
-  }
   f.in = in;
   f.n = n;
   f.nvalid = static_cast<int>(sm.nvalid);
@@ -470,7 +486,7 @@ __global__ void __launch_bounds__(kFinThreads, 2) bootstrap_select_kernel(
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
   const FinFront f = fin_front(cand_in + static_cast<int64_t>(q) * C, gath + static_cast<int64_t>(q) * C, min(cnt[q], S), S,
-                               cap_p, max_pairs, cnt2 + q * max_pairs, k, margin[q], fin_buf, P, sm);
+                               cap_p, max_pairs, cnt2 + q * max_pairs, k, margin[q], 0ull, fin_buf, P, sm);
   uint64_t* out = cand_out + static_cast<int64_t>(q) * C;
   // survivors -> [0, S) of the other list
   for (int i0 = 0; i0 < f.n; i0 += kFinThreads) {
@@ -493,7 +509,7 @@ __global__ void __launch_bounds__(kFinThreads, 2) bootstrap_select_kernel(
 #pragma unroll
   for (int s2 = 16; s2 >= 1; s2 >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, s2));
   if (tid == 0) sm.digit = 0;
-  if (tid < kTightenBuckets) sm.hist[tid] = 0;
+  for (int b = tid; b < kTightenBuckets; b += kFinThreads) sm.hist[b] = 0;
   __syncthreads();
   if (lane == 0) atomicMax(&sm.digit, kmax);
   __syncthreads();
@@ -512,7 +528,7 @@ __global__ void __launch_bounds__(kFinThreads, 2) bootstrap_select_kernel(
     }
   }
   __syncthreads();
-  if (tid < kTightenBuckets) hist[static_cast<int64_t>(q) * kTightenBuckets + tid] = sm.hist[tid];
+  for (int b = tid; b < kTightenBuckets; b += kFinThreads) hist[static_cast<int64_t>(q) * kTightenBuckets + b] = sm.hist[b];
   for (int p = tid; p < max_pairs; p += kFinThreads) cnt2[q * max_pairs + p] = 0;
   if (tid == 0) {
     const int msurv = static_cast<int>(sm.count);
@@ -529,8 +545,9 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
     const float* __restrict__ margin, int S, int cap_p, int max_pairs, const int* __restrict__ cnt2,
     const int* __restrict__ ovf, int* __restrict__ ovf_out, const float* __restrict__ q32,
     const float* __restrict__ x32, const Seg* __restrict__ segs, int nseg, const int64_t* __restrict__ idmap,
-    float* __restrict__ D_out, int64_t* __restrict__ I_out, int64_t out_stride, int P) {
-  extern __shared__ __align__(16) uint64_t fin_buf[];   // [2][P]
+    float* __restrict__ D_out, int64_t* __restrict__ I_out, int64_t out_stride, int P,
+    const float* __restrict__ tau_low /* [nq] lower bounds of the survivor thresholds, or null */) {
+  extern __shared__ __align__(16) uint64_t fin_buf[];   // [P] gathered list, then the survivors
   __shared__ FinSmem sm;
   __shared__ __align__(16) float Qs[kD];
   const int q = blockIdx.x;
@@ -538,7 +555,8 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
   uint64_t* bufB = fin_buf + P;
   for (int i = tid; i < kD; i += kFinThreads) Qs[i] = q32[static_cast<int64_t>(q) * kD + i];
   const FinFront f = fin_front(cand + static_cast<int64_t>(q) * C, gath + static_cast<int64_t>(q) * C, min(cnt[q], S), S, cap_p,
-                               max_pairs, cnt2 + q * max_pairs, k, margin[q], fin_buf, P, sm);
+                               max_pairs, cnt2 + q * max_pairs, k, margin[q],
+                               tau_low ? static_cast<uint64_t>(fkey(tau_low[q])) << 32 : 0ull, fin_buf, P, sm);
   const uint64_t* in = f.in;
   const int n = f.n;
   const uint64_t T = f.T;

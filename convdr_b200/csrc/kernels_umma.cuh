@@ -40,7 +40,7 @@ constexpr int kTmemColsA = kD / 2;             // 384 columns: 128 lanes x 768 b
 constexpr int kTmemColD = kTmemColsA;          // accumulators: columns [384, 512)
 constexpr int kAccStages = (kTmemCols - kTmemColsA) / kTileRows;    // 2 (double-buffered)
 constexpr int kUmmaTailBytes = 2048;           // barriers, tmem pointer
-constexpr int kHistBuckets = 128;              // tightening histogram: one uint4 per refresher lane
+constexpr int kHistBuckets = 512;              // tightening histogram: 16 buckets per refresher lane
 constexpr int kUmmaSmemBytes = kNumStages * kStageBytes + kUmmaTailBytes + 1024;  // + alignment slack
 static_assert(kUmmaSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
 static_assert(kAccStages >= 1 && kAccStages <= 2, "TMEM budget: 384 query columns + accumulators in 128 columns");
@@ -64,12 +64,19 @@ struct UmmaArgs {
   // In-kernel threshold tightening (see the refresher role below).  Every hit is also counted in a
   // per-query histogram over the score-key range above the bootstrap's k-th score:
   //   bucket(key) = min(kHistBuckets-1, (key - hkey0[q]) >> hshift[q])   for key >= hkey0[q]
-  // so "k rows seen so far score at least edge(b)" is one suffix sum away.
+  // so "k rows seen so far score at least edge(b)" is one suffix sum away.  Two ways to place the
+  // buckets (host option "bootstrap"):
+  //   0 (default): no bootstrap at all.  hkey0 = ((fkey(R) >> 17) - 511) << 17, hshift = 17 with
+  //      R >= any |score| of the query (Cauchy-Schwarz): 64 buckets per binade (1.6 % of the score)
+  //      over the eight binades below R.  tau starts at -inf, the first tile of every pair passes
+  //      entirely, and the thresholds rise from there — ONE launch streams the whole shard.
+  //   1: a dense bootstrap launch + bootstrap_select_kernel place 512 linear buckets above the k-th
+  //      best score of the first rows.
   int tighten;                // >0: the idle warp of each CTA keeps raising tau[q] while the stream runs;
                               //     the value is the pause between its rounds in ns
   int k;
   const float* margin;        // [nq] 2*eps of the prefilter
-  unsigned int* hist;         // [nq][kHistBuckets], initialised by refresh_kernel after the bootstrap
+  unsigned int* hist;         // [nq][kHistBuckets], initialised by pass_init_kernel / bootstrap_select_kernel
   const uint32_t* hkey0;      // [nq] key of the bootstrap's k-th best approximate score (0xffffffff: none yet)
   const int* hshift;          // [nq] log2(keys per bucket)
 };
@@ -486,8 +493,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
       for (int q = blockIdx.x; q < a.nq; q += gridDim.x, ++qi) {
         const uint32_t key0 = a.hkey0[q];
         if (key0 == 0xffffffffu) continue;     // fewer than k rows seen by the bootstrap: nothing to reject
-        const uint4 h = __ldcv(reinterpret_cast<const uint4*>(a.hist + static_cast<int64_t>(q) * kHistBuckets) + lane);
-        const unsigned int mine = h.x + h.y + h.z + h.w;
+        // lane l owns buckets [16l, 16l+16)
+        const uint4* hp = reinterpret_cast<const uint4*>(a.hist + static_cast<int64_t>(q) * kHistBuckets) + 4 * lane;
+        uint4 h4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h4[u] = __ldcv(hp + u);
+        unsigned int mine = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mine += h4[u].x + h4[u].y + h4[u].z + h4[u].w;
         unsigned int suf = mine;               // hits in the buckets of lanes >= this one
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -497,11 +510,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
         const unsigned int kk = static_cast<unsigned int>(a.k);
         unsigned int above = suf - mine;
         int b = -1;
-        if (suf >= kk && above < kk) {         // exactly one lane
-          above += h.w; b = 4 * lane + 3;
-          if (above < kk) { above += h.z; b = 4 * lane + 2; }
-          if (above < kk) { above += h.y; b = 4 * lane + 1; }
-          if (above < kk) { b = 4 * lane; }
+        if (suf >= kk && above < kk) {         // exactly one lane: walk its 16 buckets from the top
+#pragma unroll
+          for (int u = 3; u >= 0; --u) {
+            const unsigned int c4[4] = {h4[u].x, h4[u].y, h4[u].z, h4[u].w};
+#pragma unroll
+            for (int j = 3; j >= 0; --j) {
+              if (b < 0) {
+                above += c4[j];
+                if (above >= kk) b = 16 * lane + 4 * u + j;
+              }
+            }
+          }
         }
         const unsigned int who = __ballot_sync(0xffffffffu, b >= 0);
         if (who == 0u) continue;
