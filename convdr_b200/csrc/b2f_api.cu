@@ -212,9 +212,10 @@ struct b2f_index {
   int umma_variant = 0;   // 0 auto, 1 smem-stationary queries (SS), 2 TMEM-stationary queries (TS)
   int l2_prefetch = 1;
   int worst_case_margin = 0;  // 1: bf16 margin from the data-independent worst case (A/B only)
+  int tighten_adaptive = 1;  // refresher pause grows with the elapsed kernel time (see UmmaArgs)
   int bootstrap = 0;      // TS engine with tightening: 1 = dense bootstrap launch + bootstrap_select_kernel before the
                           // main launch, 0 = none (thresholds start at -inf inside the single launch)
-  int tighten = 400;      // TS engine: in-kernel threshold tightening through a global hit histogram (one
+  int tighten = 2000;      // TS engine: in-kernel threshold tightening through a global hit histogram (one
                           // launch after the bootstrap); pause of the refresher between rounds in ns,
                           // 0 = off (geometric phases with a refresh kernel between them).
   Stats stats;
@@ -349,7 +350,7 @@ int ensure_pass_ws(Shard& S, int qp, int C) {
   dev_free(W.hist); dev_free(W.hkey0); dev_free(W.hshift);
   B2F_TRY(dev_alloc(&W.gath, static_cast<size_t>(qp) * C));
   B2F_TRY(dev_alloc(&W.cnt2, static_cast<size_t>(qp) * 128));
-  B2F_TRY(dev_alloc(&W.hist, static_cast<size_t>(qp) * kHistBuckets));
+  B2F_TRY(dev_alloc(&W.hist, static_cast<size_t>(qp) * kHistStride));
   B2F_TRY(dev_alloc(&W.hkey0, static_cast<size_t>(qp)));
   B2F_TRY(dev_alloc(&W.hshift, static_cast<size_t>(qp)));
   B2F_TRY(dev_alloc(&W.cand[0], static_cast<size_t>(qp) * C));
@@ -400,7 +401,7 @@ __global__ void pass_init_kernel(const float* __restrict__ qnorm, const float* _
   if (hist != nullptr) {
     // TS engine without a bootstrap launch: empty tightening histogram of 64 buckets per binade over
     // the eight binades below R = (1 + 2^-6) * ||q|| * max||p|| >= |any prefilter score of q|; tau = -inf.
-    for (int b = threadIdx.x; b < kHistBuckets; b += blockDim.x) hist[static_cast<int64_t>(q) * kHistBuckets + b] = 0u;
+    for (int b = threadIdx.x; b < kHistStride; b += blockDim.x) hist[static_cast<int64_t>(q) * kHistStride + b] = 0u;
     if (threadIdx.x == 0) {
       const float R = __fmul_ru(__fmul_ru(qnorm[q], __fsqrt_ru(__uint_as_float(maxnorm2_bits[0]))), 1.015625f);
       const uint32_t top = fkey(R) >> 17;
@@ -607,7 +608,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       a.n_rows = N; a.tile_begin = tb; a.tile_end = te; a.nq = nqp; a.q16 = q16p;
       a.dense = dense ? 1 : 0; a.cand = W.cand[cur]; a.C = C; a.S = plan.S; a.cap_p = plan.cap_p;
       a.max_pairs = S.max_pairs; a.cnt2 = W.cnt2; a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
-      a.tighten = idx->tighten; a.k = k; a.margin = W.margin; a.hist = W.hist; a.hkey0 = W.hkey0; a.hshift = W.hshift;
+      a.tighten = idx->tighten; a.tighten_adaptive = idx->tighten_adaptive; a.k = k; a.margin = W.margin; a.hist = W.hist; a.hkey0 = W.hkey0; a.hshift = W.hshift;
       const int pairs = std::min(S.max_pairs, te - tb);
       {
         ProfScope ps(idx, S, 0);
@@ -1331,6 +1332,8 @@ int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
   } else if (k == "tighten") {
     if (value < 0 || value > 1000000) return fail(B2F_ERR_INVALID, "tighten must be 0 (off) or a pause in ns <= 1e6");
     idx->tighten = static_cast<int>(value);
+  } else if (k == "tighten_adaptive") {
+    idx->tighten_adaptive = value ? 1 : 0;
   } else if (k == "bootstrap") {
     idx->bootstrap = value ? 1 : 0;
   } else if (k == "worst_case_margin") {

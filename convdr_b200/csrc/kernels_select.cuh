@@ -13,6 +13,7 @@ namespace b2f {
 constexpr int kSelThreads = 256;
 constexpr int kSortCap = 2048;  // == B2F_MAX_K
 constexpr int kTightenBuckets = 512;  // == kHistBuckets of kernels_umma.cuh
+constexpr int kTightenStride = kTightenBuckets + kTightenBuckets / 16;  // == kHistStride: [512 fine][32 coarse] per query
 
 struct Seg {  // rows [local_start, local_start+count) of a shard carry ids global_start + i
   int64_t local_start, count, global_start;
@@ -227,7 +228,12 @@ __global__ void __launch_bounds__(kSelThreads) refresh_kernel(
     }
     __syncthreads();
     for (int b = threadIdx.x; b < kTightenBuckets; b += kSelThreads)
-      hist[static_cast<int64_t>(q) * kTightenBuckets + b] = sm.hist[b];
+      hist[static_cast<int64_t>(q) * kTightenStride + b] = sm.hist[b];
+    if (threadIdx.x < kTightenBuckets / 16) {
+      unsigned int c = 0;
+      for (int j = 0; j < 16; ++j) c += sm.hist[16 * threadIdx.x + j];
+      hist[static_cast<int64_t>(q) * kTightenStride + kTightenBuckets + threadIdx.x] = c;
+    }
     if (threadIdx.x == 0) { hkey0[q] = key0; hshift[q] = shift; }
   }
 }
@@ -528,7 +534,12 @@ __global__ void __launch_bounds__(kFinThreads, 2) bootstrap_select_kernel(
     }
   }
   __syncthreads();
-  for (int b = tid; b < kTightenBuckets; b += kFinThreads) hist[static_cast<int64_t>(q) * kTightenBuckets + b] = sm.hist[b];
+  for (int b = tid; b < kTightenBuckets; b += kFinThreads) hist[static_cast<int64_t>(q) * kTightenStride + b] = sm.hist[b];
+  if (tid < kTightenBuckets / 16) {
+    unsigned int c = 0;
+    for (int j = 0; j < 16; ++j) c += sm.hist[16 * tid + j];
+    hist[static_cast<int64_t>(q) * kTightenStride + kTightenBuckets + tid] = c;
+  }
   for (int p = tid; p < max_pairs; p += kFinThreads) cnt2[q * max_pairs + p] = 0;
   if (tid == 0) {
     const int msurv = static_cast<int>(sm.count);

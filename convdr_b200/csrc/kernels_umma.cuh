@@ -41,6 +41,8 @@ constexpr int kTmemColD = kTmemColsA;          // accumulators: columns [384, 51
 constexpr int kAccStages = (kTmemCols - kTmemColsA) / kTileRows;    // 2 (double-buffered)
 constexpr int kUmmaTailBytes = 2048;           // barriers, tmem pointer
 constexpr int kHistBuckets = 512;              // tightening histogram: 16 buckets per refresher lane
+constexpr int kHistCoarse = kHistBuckets / 16; // + one coarse counter per lane (sum of its 16 buckets)
+constexpr int kHistStride = kHistBuckets + kHistCoarse;   // uints per query: [512 fine][32 coarse]
 constexpr int kUmmaSmemBytes = kNumStages * kStageBytes + kUmmaTailBytes + 1024;  // + alignment slack
 static_assert(kUmmaSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
 static_assert(kAccStages >= 1 && kAccStages <= 2, "TMEM budget: 384 query columns + accumulators in 128 columns");
@@ -73,10 +75,14 @@ struct UmmaArgs {
   //   1: a dense bootstrap launch + bootstrap_select_kernel place 512 linear buckets above the k-th
   //      best score of the first rows.
   int tighten;                // >0: the idle warp of each CTA keeps raising tau[q] while the stream runs;
-                              //     the value is the pause between its rounds in ns
+                              //     the value is the minimum pause between its rounds in ns
+  int tighten_adaptive;       // 1: the pause grows with the time since the kernel started (elapsed / 4, capped at
+                              //     50 us): the pass rate falls like k / rows_seen, so a threshold of bounded
+                              //     relative age costs a bounded fraction of extra hits whatever the moment,
+                              //     and a launch needs ~50 polling rounds instead of thousands
   int k;
   const float* margin;        // [nq] 2*eps of the prefilter
-  unsigned int* hist;         // [nq][kHistBuckets], initialised by pass_init_kernel / bootstrap_select_kernel
+  unsigned int* hist;         // [nq][kHistStride], initialised by pass_init_kernel / bootstrap_select_kernel
   const uint32_t* hkey0;      // [nq] key of the bootstrap's k-th best approximate score (0xffffffff: none yet)
   const int* hshift;          // [nq] log2(keys per bucket)
 };
@@ -388,13 +394,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     const bool live = a.tighten && q_ok && !a.dense;
     const uint32_t hkey0 = live ? a.hkey0[q] : 0xffffffffu;
     const int hshift = live ? a.hshift[q] : 0;
-    unsigned int* my_hist = a.hist + static_cast<int64_t>(q_ok ? q : 0) * kHistBuckets;
+    unsigned int* my_hist = a.hist + static_cast<int64_t>(q_ok ? q : 0) * kHistStride;
     uint64_t* my_list = a.cand + static_cast<int64_t>(q_ok ? q : 0) * a.C + a.S + static_cast<int64_t>(pair) * a.cap_p;
     int n_mine = 0;   // entries this thread appended for (query q, this pair)
     // count a hit in the tightening histogram (fire-and-forget RED; hits are rare)
     auto count_hit = [&](uint32_t bits) {
       const uint32_t key = fkey(__uint_as_float(bits));
-      if (key >= hkey0) atomicAdd(my_hist + min(static_cast<uint32_t>(kHistBuckets - 1), (key - hkey0) >> hshift), 1u);
+      if (key >= hkey0) {
+        const uint32_t b = min(static_cast<uint32_t>(kHistBuckets - 1), (key - hkey0) >> hshift);
+        atomicAdd(my_hist + b, 1u);
+        atomicAdd(my_hist + kHistBuckets + (b >> 4), 1u);
+      }
     };
     const uint32_t tempty_leader = mapa_u32(bar_tempty, 0);
     int it = 0;
@@ -488,19 +498,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     // every pair because all thresholds in use are <= the current one.  Effect: the pass rate
     // follows k/rows_seen continuously, so ONE launch streams the whole shard after the bootstrap.
     float last[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    const long long t_start = clock64();
     while (*epi_done_s < 4) {
       int qi = 0;
       for (int q = blockIdx.x; q < a.nq; q += gridDim.x, ++qi) {
         const uint32_t key0 = a.hkey0[q];
         if (key0 == 0xffffffffu) continue;     // fewer than k rows seen by the bootstrap: nothing to reject
-        // lane l owns buckets [16l, 16l+16)
-        const uint4* hp = reinterpret_cast<const uint4*>(a.hist + static_cast<int64_t>(q) * kHistBuckets) + 4 * lane;
-        uint4 h4[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) h4[u] = __ldcv(hp + u);
-        unsigned int mine = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) mine += h4[u].x + h4[u].y + h4[u].z + h4[u].w;
+        // lane l owns buckets [16l, 16l+16).  One 128-byte read of the 32 coarse counters per round; only
+        // the lane where the suffix sum crosses k reads its 16 fine buckets (192 B per query and round
+        // instead of 2 KB: the polling shares the L2 -> SM path with the 6 TB/s passage stream).
+        const unsigned int* hq = a.hist + static_cast<int64_t>(q) * kHistStride;
+        const unsigned int mine = __ldcv(hq + kHistBuckets + lane);
         unsigned int suf = mine;               // hits in the buckets of lanes >= this one
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -510,10 +518,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
         const unsigned int kk = static_cast<unsigned int>(a.k);
         unsigned int above = suf - mine;
         int b = -1;
-        if (suf >= kk && above < kk) {         // exactly one lane: walk its 16 buckets from the top
+        if (suf >= kk && above < kk) {         // exactly one lane: walk its 16 fine buckets from the top
+          const uint4* hp = reinterpret_cast<const uint4*>(hq) + 4 * lane;
 #pragma unroll
           for (int u = 3; u >= 0; --u) {
-            const unsigned int c4[4] = {h4[u].x, h4[u].y, h4[u].z, h4[u].w};
+            const uint4 h4 = __ldcv(hp + u);
+            const unsigned int c4[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
             for (int j = 3; j >= 0; --j) {
               if (b < 0) {
@@ -538,7 +548,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
           }
         }
       }
-      __nanosleep(static_cast<unsigned int>(a.tighten));
+      unsigned int pause = static_cast<unsigned int>(a.tighten);
+      if (a.tighten_adaptive) {
+        const long long age_ns = (clock64() - t_start) >> 1;     // cycles -> ns at ~2 GHz; only a pacing hint
+        pause = static_cast<unsigned int>(min(max(static_cast<long long>(pause), age_ns >> 2), 50000ll));
+      }
+      __nanosleep(pause);
     }
   }
   __syncwarp();

@@ -1,5 +1,5 @@
 """Batch-size sweep on one GPU (BASELINE.json config 5 shape): ms per search and streamed GB/s for the
-SIMT scan and the tensor engine, device-resident queries.  Usage: python tools/sweep.py ROWS K OUT.json"""
+SIMT scan and the tensor engine, device-resident queries, searches queued back to back.  Usage: python tools/sweep.py ROWS K OUT.json"""
 import json
 import os
 import sys
@@ -34,19 +34,21 @@ def main():
             reps = 3 if (path == "scan_f32" and nq > 16) else 8
             for _ in range(2):
                 idx.search_device_into(q, k, D, I)
+            idx.reset_stats()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            sc = 0.0
             for _ in range(reps):
-                idx.search_device_into(q, k, D, I)
-                sc += idx.stat("score_ms")
+                idx.search_device_async(q, k, D, I)     # queued back to back, settled once
+            idx.finish()
             e1.record(stream)
             torch.cuda.synchronize()
+            sc = idx.stat("score_ms")
             ms = e0.elapsed_time(e1) / reps
             bpr = 3072 if path == "scan_f32" else 1536
-            passes = idx.stat("passes")
+            passes = idx.stat("passes") / reps
             r = dict(nq=nq, k=k, rows=rows, path=path, ms=ms, qps=nq / ms * 1e3, score_ms=sc / reps, passes=passes,
                      streamed_gbs=rows * bpr * passes / (sc / reps * 1e-3) / 1e9 if sc > 0 else None,
+                     useful_tflops=2.0 * nq * rows * 768 / (ms * 1e-3) / 1e12,
                      fallback=idx.stat("fallback_queries"))
             res.append(r)
             print(json.dumps(r), flush=True)
