@@ -15,6 +15,11 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -173,9 +178,59 @@ struct Shard {
   int segs_d_cap = 0;
   Workspace ws;
   Prof prof;
+  Stats stats;
+  bool peer_to_first = false;   // this device can store into shard 0's device memory (in-process result gather)
 };
 
 }  // namespace
+
+// One persistent host thread per shard beyond the first: a multi-device search is enqueued on all
+// devices at the same time (FAISS IndexShards runs one host thread per GPU shard too) instead of
+// paying the launch sequence of every device one after the other.
+struct ShardWorker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<int()> task;
+  bool has_task = false, done = false, stop = false;
+  int rc = 0;
+  std::string err;
+  void loop() {
+    std::unique_lock<std::mutex> lk(m);
+    for (;;) {
+      cv.wait(lk, [&] { return has_task || stop; });
+      if (stop) return;
+      lk.unlock();
+      const int r = task();
+      lk.lock();
+      rc = r;
+      err = g_err;            // the worker's thread-local error text travels back with the code
+      has_task = false;
+      done = true;
+      cv.notify_all();
+    }
+  }
+  void submit(std::function<int()> f) {
+    std::lock_guard<std::mutex> lk(m);
+    task = std::move(f);
+    has_task = true;
+    done = false;
+    cv.notify_all();
+  }
+  int wait() {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return done; });
+    done = false;
+    if (rc != B2F_OK) g_err = err;
+    return rc;
+  }
+  ~ShardWorker() {
+    if (th.joinable()) {
+      { std::lock_guard<std::mutex> lk(m); stop = true; cv.notify_all(); }
+      th.join();
+    }
+  }
+};
 
 struct Pending {
   const float* q; int64_t nq; int k; float* D; int64_t* I; int slot;
@@ -185,6 +240,7 @@ struct b2f_index {
   int d = kD;
   std::vector<Shard> shards;
   std::vector<Pending> pending;   // enqueued by b2f_search_device_async, settled by b2f_search_finish
+  std::vector<std::unique_ptr<ShardWorker>> workers;   // [shards - 1], created by the first multi-shard search
   int* merge_flag_host = nullptr; // mapped host ints: [0] a merge saw a part whose list had overflowed,
   int* merge_flag_dev = nullptr;  //                   [1] the peer exchange timed out waiting for a rank
   // peer-memory exchange (one process per GPU; see kernels_select.cuh)
@@ -455,8 +511,8 @@ void collect_prof(b2f_index* idx, Shard& S) {
   for (const Prof::Span& sp : P.spans) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, P.pool[sp.b], P.pool[sp.e]) == cudaSuccess) {
-      if (sp.kind == 0) { idx->stats.score_ms += ms; idx->stats.score_launches += 1; }
-      else idx->stats.select_ms += ms;
+      if (sp.kind == 0) { S.stats.score_ms += ms; S.stats.score_launches += 1; }
+      else S.stats.select_ms += ms;
     } else {
       (void)cudaGetLastError();
     }
@@ -531,7 +587,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
                  const float* qnormp, const float* qerrp, int nqp, int k, float* D_out, int64_t* I_out, int64_t out_stride,
                  int* ovf_dst) {
   Workspace& W = S.ws;
-  Stats& st = idx->stats;
+  Stats& st = S.stats;   // per shard: shards may be enqueued from different host threads
   const int64_t N = S.n;
   const int C = W.C;
   cudaStream_t s = S.stream;
@@ -718,7 +774,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
     return B2F_OK;
   }
   const int path = resolve_path(idx, S, nq);
-  idx->stats.path = path;
+  S.stats.path = path;
   const PassPlan plan = make_plan(idx, S, path, k, nq);
   B2F_TRY(ensure_pass_ws(S, plan.qp, plan.C));
   B2F_TRY(upload_segs(S));
@@ -726,7 +782,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
   prep_queries_kernel<<<static_cast<int>((nq_pad * 32 + 127) / 128), 128, 0, s>>>(
       q_d, static_cast<int>(nq), static_cast<int>(nq_pad), W.q16, W.qnorm, W.qerr);
   CU_TRY(cudaGetLastError());
-  idx->stats.launches += 1;
+  S.stats.launches += 1;
   if (plan.path == B2F_PATH_UMMA_BF16) {
     static bool attr_set[64] = {false};
     if (!attr_set[S.dev & 63]) {
@@ -768,7 +824,7 @@ int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k,
     if (flags[q]) bad.push_back(q);
   if (bad.empty()) return B2F_OK;
   if (reran) *reran = true;
-  idx->stats.fallback_queries += static_cast<double>(bad.size());
+  S.stats.fallback_queries += static_cast<double>(bad.size());
   static bool attr_set3[64] = {false};
   if (!attr_set3[S.dev & 63]) {
     CU_TRY(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
@@ -793,6 +849,29 @@ int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k,
   CU_TRY(cudaStreamSynchronize(s));
   if (idx->profile) collect_prof(idx, S);
   return B2F_OK;
+}
+
+// Run fn(g) for every shard: shard 0 on the calling thread, the others on their workers.  Returns the
+// first failure (its error text becomes this thread's b2f_last_error()).
+int run_on_shards(b2f_index* idx, const std::function<int(int)>& fn) {
+  const int G = static_cast<int>(idx->shards.size());
+  if (G == 1) return fn(0);
+  if (idx->workers.empty()) {
+    for (int g = 1; g < G; ++g) {
+      idx->workers.emplace_back(new ShardWorker());
+      ShardWorker* w = idx->workers.back().get();
+      w->th = std::thread([w] { w->loop(); });
+    }
+  }
+  for (int g = 1; g < G; ++g) idx->workers[g - 1]->submit([&fn, g] { return fn(g); });
+  int rc = fn(0);
+  std::string err0 = rc != B2F_OK ? g_err : std::string();
+  for (int g = 1; g < G; ++g) {
+    const int r = idx->workers[g - 1]->wait();
+    if (rc == B2F_OK && r != B2F_OK) { rc = r; err0 = g_err; }
+  }
+  if (rc != B2F_OK) g_err = err0;
+  return rc;
 }
 
 // Settle every search enqueued by b2f_search_device_async: wait for the stream, then re-run (on the
@@ -823,7 +902,10 @@ int check_args_search(const b2f_index* idx, const void* q, int64_t nq, int k, co
   return B2F_OK;
 }
 
-void reset_stats(b2f_index* idx) { idx->stats = Stats(); }
+void reset_stats(b2f_index* idx) {
+  idx->stats = Stats();
+  for (Shard& S : idx->shards) S.stats = Stats();
+}
 
 }  // namespace
 
@@ -900,8 +982,10 @@ int b2f_create(int d, const int* devices, int n_dev, b2f_index** out) {
         cudaSetDevice(devs[i]);
         cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
         if (e != cudaSuccess) (void)cudaGetLastError();
+        if (j == 0 && (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled)) idx->shards[i].peer_to_first = true;
       }
     }
+  (void)get_encode_fn();   // resolve the driver entry point before any worker thread needs it
   *out = idx;
   return B2F_OK;
 }
@@ -909,6 +993,7 @@ int b2f_create(int d, const int* devices, int n_dev, b2f_index** out) {
 void b2f_destroy(b2f_index* idx) {
   if (!idx) return;
   idx->pending.clear();
+  idx->workers.clear();      // joins the shard threads
   for (Shard& S : idx->shards) {
     cudaSetDevice(S.dev);
     if (S.stream) cudaStreamSynchronize(S.stream);
@@ -970,11 +1055,12 @@ static int add_impl(b2f_index* idx, const float* x_host, const int64_t* ids_host
     for (Shard& S : idx->shards)
       if (S.has_ids && S.n > 0) return fail(B2F_ERR_INVALID, "cannot mix add_with_ids() and add() on a non-empty index");
   }
-  // contiguous split, like FAISS IndexShards with successive ids
-  for (int g = 0; g < G; ++g) {
+  // contiguous split, like FAISS IndexShards with successive ids; every device copies and ingests its
+  // slice from its own host thread, so the PCIe links of all GPUs run in parallel
+  B2F_TRY(run_on_shards(idx, [&](int g) -> int {
     Shard& S = idx->shards[g];
     const int64_t lo = n * g / G, hi = n * (g + 1) / G, m = hi - lo;
-    if (m == 0) continue;
+    if (m == 0) return B2F_OK;
     CU_TRY(cudaSetDevice(S.dev));
     if (ids_host && !S.has_ids) {
       S.has_ids = true;
@@ -990,11 +1076,9 @@ static int add_impl(b2f_index* idx, const float* x_host, const int64_t* ids_host
     B2F_TRY(ingest_rows(idx, S, m));
     push_seg(S, S.n, m, idx->ntotal + lo);
     S.n += m;
-  }
-  for (Shard& S : idx->shards) {
-    CU_TRY(cudaSetDevice(S.dev));
     CU_TRY(cudaStreamSynchronize(S.stream));  // FAISS add() is synchronous: the caller may free x now
-  }
+    return B2F_OK;
+  }));
   idx->ntotal += n;
   return B2F_OK;
 }
@@ -1240,13 +1324,28 @@ int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_
   CU_TRY(cudaSetDevice(S0.dev));
   B2F_TRY(ensure_pin(S0, std::max(qbytes, obytes)));
   std::memcpy(S0.ws.pin, q_host, qbytes);
-  for (int g = 0; g < G; ++g) {
+  const int64_t per = nq * k;
+  if (G > 1) {   // gather area on the first device: parts [G][nq][k] + the merged result
+    Workspace& W = S0.ws;
+    if (per * (G + 1) > W.parts_cap) {
+      dev_free(W.Dp); dev_free(W.Ip);
+      B2F_TRY(dev_alloc(&W.Dp, static_cast<size_t>(per) * (G + 1)));
+      B2F_TRY(dev_alloc(&W.Ip, static_cast<size_t>(per) * (G + 1)));
+      W.parts_cap = per * (G + 1);
+    }
+  }
+  // Where shard g leaves its [nq,k] lists: a shard whose device can store into the first device's
+  // memory writes its part of the gather area directly (the last kernel of the search pushes the rows
+  // over NVLink as it produces them); otherwise its own buffer + a peer copy below.
+  auto part_D = [&](int g) { return (G > 1 && (g == 0 || idx->shards[g].peer_to_first)) ? S0.ws.Dp + per * g : idx->shards[g].ws.D; };
+  auto part_I = [&](int g) { return (G > 1 && (g == 0 || idx->shards[g].peer_to_first)) ? S0.ws.Ip + per * g : idx->shards[g].ws.I; };
+  B2F_TRY(run_on_shards(idx, [&](int g) -> int {   // every device is enqueued by its own host thread
     Shard& S = idx->shards[g];
     CU_TRY(cudaSetDevice(S.dev));
     B2F_TRY(ensure_query_ws(S, nq, k));
     CU_TRY(cudaMemcpyAsync(S.ws.q32, S0.ws.pin, qbytes, cudaMemcpyHostToDevice, S.stream));
-    B2F_TRY(enqueue_search(idx, S, S.ws.q32, nq, k, S.ws.D, S.ws.I));
-  }
+    return enqueue_search(idx, S, S.ws.q32, nq, k, part_D(g), part_I(g));
+  }));
   float* pinD = reinterpret_cast<float*>(S0.ws.pin);
   int64_t* pinI = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(S0.ws.pin) + d_off);
   if (G == 1) {
@@ -1267,31 +1366,21 @@ int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_
   }
   for (int g = 0; g < G; ++g) {
     Shard& S = idx->shards[g];
-    B2F_TRY(finish_search(idx, S, S.ws.q32, nq, k, S.ws.D, S.ws.I));
+    B2F_TRY(finish_search(idx, S, S.ws.q32, nq, k, part_D(g), part_I(g)));
   }
   CU_TRY(cudaSetDevice(S0.dev));
-  const float* Dres = S0.ws.D;
-  const int64_t* Ires = S0.ws.I;
-  if (G > 1) {
-    Workspace& W = S0.ws;
-    const int64_t per = nq * k;
-    if (per * (G + 1) > W.parts_cap) {
-      dev_free(W.Dp); dev_free(W.Ip);
-      B2F_TRY(dev_alloc(&W.Dp, static_cast<size_t>(per) * (G + 1)));
-      B2F_TRY(dev_alloc(&W.Ip, static_cast<size_t>(per) * (G + 1)));
-      W.parts_cap = per * (G + 1);
-    }
-    for (int g = 0; g < G; ++g) {
-      Shard& S = idx->shards[g];
-      CU_TRY(cudaMemcpyPeerAsync(W.Dp + per * g, S0.dev, S.ws.D, S.dev, sizeof(float) * per, S0.stream));
-      CU_TRY(cudaMemcpyPeerAsync(W.Ip + per * g, S0.dev, S.ws.I, S.dev, sizeof(int64_t) * per, S0.stream));
-    }
-    merge_kernel<<<static_cast<int>(nq), 256, 0, S0.stream>>>(W.Dp, W.Ip, G, nq, k, W.Dp + per * G, W.Ip + per * G, per, per, nullptr);
-    CU_TRY(cudaGetLastError());
-    idx->stats.launches += 1;
-    Dres = W.Dp + per * G;
-    Ires = W.Ip + per * G;
+  Workspace& W = S0.ws;
+  for (int g = 1; g < G; ++g) {
+    Shard& S = idx->shards[g];
+    if (S.peer_to_first) continue;
+    CU_TRY(cudaMemcpyPeerAsync(W.Dp + per * g, S0.dev, S.ws.D, S.dev, sizeof(float) * per, S0.stream));
+    CU_TRY(cudaMemcpyPeerAsync(W.Ip + per * g, S0.dev, S.ws.I, S.dev, sizeof(int64_t) * per, S0.stream));
   }
+  merge_kernel<<<static_cast<int>(nq), 256, 0, S0.stream>>>(W.Dp, W.Ip, G, nq, k, W.Dp + per * G, W.Ip + per * G, per, per, nullptr);
+  CU_TRY(cudaGetLastError());
+  idx->stats.launches += 1;
+  const float* Dres = W.Dp + per * G;
+  const int64_t* Ires = W.Ip + per * G;
   CU_TRY(cudaMemcpyAsync(pinD, Dres, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
   CU_TRY(cudaMemcpyAsync(pinI, Ires, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
   CU_TRY(cudaStreamSynchronize(S0.stream));
@@ -1352,7 +1441,17 @@ int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
 int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
   if (!idx || !key || !out) return fail(B2F_ERR_INVALID, "bad stat arguments");
   const std::string k(key);
-  const Stats& s = idx->stats;
+  Stats s = idx->stats;          // index-level counters (merges, exchange) + the sum over shards
+  for (const Shard& S : idx->shards) {
+    s.launches += S.stats.launches; s.phases += S.stats.phases; s.candidates += S.stats.candidates;
+    s.fallback_queries += S.stats.fallback_queries; s.passes += S.stats.passes; s.score_ms += S.stats.score_ms;
+    s.score_launches += S.stats.score_launches; s.score_rows += S.stats.score_rows; s.select_ms += S.stats.select_ms;
+  }
+  if (!idx->shards.empty()) {
+    s.path = idx->shards[0].stats.path;
+    s.passes = idx->shards[0].stats.passes;   // passes / phases are per search, not per shard
+    s.phases = idx->shards[0].stats.phases;
+  }
   if (k == "launches") *out = s.launches;
   else if (k == "phases") *out = s.phases;
   else if (k == "candidates") *out = s.candidates;
