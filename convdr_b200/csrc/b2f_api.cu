@@ -1191,7 +1191,13 @@ int b2f_search_device_async(b2f_index* idx, const float* q_dev, int64_t nq, int 
 
 int b2f_search_finish(b2f_index* idx) {
   if (!idx) return fail(B2F_ERR_INVALID, "null index");
-  return settle_pending(idx);
+  B2F_TRY(settle_pending(idx));
+  // also wait for work queued behind the searches (exchange push / merge kernels, a re-push)
+  for (Shard& S : idx->shards) {
+    CU_TRY(cudaSetDevice(S.dev));
+    CU_TRY(cudaStreamSynchronize(S.stream));
+  }
+  return B2F_OK;
 }
 
 int b2f_merge_device(b2f_index* idx, const float* D_parts_dev, const int64_t* I_parts_dev, int n_parts,
