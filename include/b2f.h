@@ -167,15 +167,21 @@ int b2f_num_shards(const b2f_index* idx);
 /* Raw CUDA stream (cudaStream_t) of shard `shard`, for event timing in bench.py. */
 void* b2f_stream(b2f_index* idx, int shard);
 
-/* Tuning knobs: "path" (B2F_PATH_*), "shadow" (keep the bf16 copy, default 1),
- * "growth" (phase growth factor), "margin_ppm" (scale of the rigorous error
- * margin in parts-per-million, default 1000000), "keep_on_reset" (default 1),
- * "scan_max_auto" (largest batch AUTO sends to the SIMT scan, default 4),
- * "profile" (1: CUDA events around every scoring / selection launch),
- * "tighten" (TS tensor engine: in-kernel threshold tightening, pause of the
- * refresher warp in ns; 0 = geometric phases), "umma_variant" (0 auto, 1 SS,
- * 2 TS), "l2_prefetch" (SS variant: prefetch distance in tiles),
- * "reset_stats" (any value: zero the counters below).                          */
+/* Tuning knobs:
+ *   "path" (B2F_PATH_*), "shadow" (keep the bf16 copy, default 1), "keep_on_reset" (default 1),
+ *   "scan_max_auto" (largest batch AUTO sends to the SIMT scan, default 4),
+ *   "margin_ppm" (scale of the rigorous error margin in parts-per-million, default 1000000),
+ *   "worst_case_margin" (1: data-independent 2^-8 bound instead of the per-shard rounding-error
+ *       bound; A/B only),
+ *   "umma_variant" (tensor engine: 0 auto, 1 SS = queries in shared memory, 2 TS = queries in TMEM),
+ *   "tighten" (TS engine: in-kernel threshold tightening, minimum pause of the refresher warp in
+ *       ns, default 2000; 0 = geometric phases with a refresh kernel between them),
+ *   "tighten_adaptive" (default 1: the pause grows with the elapsed kernel time),
+ *   "bootstrap" (default 0: thresholds start at -inf inside the single launch; 1: dense bootstrap
+ *       launch + bootstrap_select_kernel first), "growth" (phase growth factor of the phased
+ *       schedules), "l2_prefetch" (SS variant: prefetch distance in tiles),
+ *   "profile" (1: CUDA events around every scoring / selection launch),
+ *   "reset_stats" (any value: zero the counters below).                          */
 int b2f_set_option(b2f_index* idx, const char* key, int64_t value);
 
 /* Counters since the last synchronous search started (asynchronous searches

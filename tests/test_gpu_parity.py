@@ -441,3 +441,30 @@ def test_peer_memory_exchange_equals_nccl_exchange(gpu_count):
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "_xchg_worker.py")]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "XCHG_OK 2" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+def test_shard_with_a_block_of_identical_rows_overflows_for_some_queries_only():
+    """1500 identical rows (> the survivor capacity) inside a shard with explicit ids: the few queries
+    that rank them high overflow, carry the marker after the asynchronous call, and are settled by
+    finish(); all others are untouched.  (The data of the 2-GPU exchange test, one shard of it.)"""
+    import torch
+    P = c_oracle.synth_block(0, 60000, seed=41)
+    P[50000:51500] = P[50000]
+    ids = np.arange(30000, 60000, dtype=np.int64)
+    idx = make_index("auto")
+    idx.add_with_ids(P[30000:], ids)
+    ref = make_index("scan_exact")
+    ref.add_with_ids(P[30000:], ids)
+    Qh = c_oracle.synth_block(0, 173, seed=3, stream=1)
+    q = torch.from_numpy(Qh).cuda()
+    D = torch.empty((173, 100), dtype=torch.float32, device="cuda")
+    I = torch.empty((173, 100), dtype=torch.int64, device="cuda")
+    idx.reset_stats()
+    idx.search_device_async(q, 100, D, I)
+    torch.cuda.synchronize()
+    marked = int((I[:, 0] == -2).sum().item())
+    idx.finish()
+    assert idx.stat("fallback_queries") == marked
+    Dr, Ir = ref.search(Qh, 100)
+    np.testing.assert_array_equal(I.cpu().numpy(), Ir)
+    np.testing.assert_array_equal(D.cpu().numpy(), Dr)
