@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--tighten", type=int, default=-1, help="-1 engine default, 0 off, >0 refresher pause in ns")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: result exchange through the engine's peer-memory kernels (default) or ncclAllGather")
+    ap.add_argument("--balance", type=int, default=1,
+                    help="N > 1: 1 = size each rank's shard by its measured local search speed (calibrated before "
+                         "the timed region), 0 = equal shards")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (A/B experiments)")
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -319,6 +322,19 @@ def run_b2f_arm(args):
     q_pin = torch.from_numpy(q_host).pin_memory()
     q_dev = q_pin.to(dev)
     nq, k = args.nq, args.k
+    balance = None
+    if world > 1 and args.balance:
+        # Speed-weighted sharding: every search waits for the slowest GPU, and the GPUs of one box differ
+        # by several percent under the power cap.  Calibrate (local search only, equal shards), then
+        # rebuild the shards with shares proportional to the measured speeds.  Setup, not timed.
+        from convdr_b200.dist import balance_weights
+        times = sharded.gather_floats(sharded.local_seconds_per_search(q_dev, k))
+        weights = balance_weights(times)
+        sharded.reset()
+        lo, hi = sharded.add_synthetic(args.rows, seed=0, stream=0, weights=weights)
+        n_local = hi - lo
+        balance = {"calibration_ms_equal_shards": [round(t * 1e3, 4) for t in times],
+                   "shares": [round(w / sum(weights), 5) for w in weights]}
     stream = torch.cuda.ExternalStream(index.stream_ptr(0), device=dev)
 
     def barrier():
@@ -364,6 +380,12 @@ def run_b2f_arm(args):
     launches, score_ms, score_launches = index.stat("launches"), index.stat("score_ms"), index.stat("score_launches")
     score_rows, select_ms = index.stat("score_rows"), index.stat("select_ms")
     fallbacks_timed = index.stat("fallback_queries")
+    per_rank = None
+    if world > 1:   # where every rank spent the step: local scoring, selection, waiting for + merging the parts
+        per_rank = {"score_ms_per_step": [round(v / args.steps, 4) for v in sharded.gather_floats(score_ms)],
+                    "select_ms_per_step": [round(v / args.steps, 4) for v in sharded.gather_floats(select_ms)],
+                    "exchange_wait_merge_ms_per_step": [round(v / args.steps, 4)
+                                                        for v in sharded.gather_floats(index.stat("xchg_ms"))]}
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -418,7 +440,7 @@ def run_b2f_arm(args):
                 "l2_policy": "inputs larger than L2 (>= 7 GB streamed per GPU per step vs 126 MB L2); no flush needed",
                 "engine_path": engine_path, "tensor_variant": args.variant, "l2_prefetch": args.l2_prefetch,
                 "build_seconds": round(build_s, 2),
-                "parallelism": f"shard{n_gpus}", "exchange": exchange,
+                "parallelism": f"shard{n_gpus}", "exchange": exchange, "balance": balance,
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -443,6 +465,7 @@ def run_b2f_arm(args):
             "e2e": {"value": nq * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(q_host.nbytes) * n_gpus,
                     "d2h_bytes_per_step": int(nq * k * 12) * n_gpus, "ms_per_step": e2e_s / args.steps * 1e3},
+            "per_rank": per_rank,
             "gpu_launches": int(stats_sum.tolist()[3]),
             "clocks": clocks,
             "check": check,

@@ -141,7 +141,7 @@ struct Workspace {
 
 struct Stats {
   double launches = 0, phases = 0, candidates = 0, fallback_queries = 0, path = 0, passes = 0;
-  double score_ms = 0, score_launches = 0, score_rows = 0, select_ms = 0;
+  double score_ms = 0, score_launches = 0, score_rows = 0, select_ms = 0, xchg_ms = 0;
 };
 
 // Optional per-launch device timing ("profile" option): CUDA events on the shard stream around
@@ -241,6 +241,7 @@ struct b2f_index {
   std::vector<Shard> shards;
   std::vector<Pending> pending;   // enqueued by b2f_search_device_async, settled by b2f_search_finish
   std::vector<std::unique_ptr<ShardWorker>> workers;   // [shards - 1], created by the first multi-shard search
+  int (*xchg_flush)(b2f_index*) = nullptr;   // set by b2f_xchg_connect (enqueues a deferred exchange merge)
   int* merge_flag_host = nullptr; // mapped host ints: [0] a merge saw a part whose list had overflowed,
   int* merge_flag_dev = nullptr;  //                   [1] the peer exchange timed out waiting for a rank
   // peer-memory exchange (one process per GPU; see kernels_select.cuh)
@@ -255,6 +256,11 @@ struct b2f_index {
     int* counter = nullptr;
     unsigned int seq = 0;
     bool connected = false;
+    // deferred merge: the merge of exchange step s is enqueued behind the push of step s+1 (or by
+    // b2f_search_finish), when every rank's part has long arrived, so the ranks are coupled with one
+    // step of slack instead of a barrier per search (they all wait for the momentarily slowest GPU otherwise)
+    int defer = 1;
+    struct Deferred { bool valid = false; unsigned int seq = 0; int64_t nq = 0; int k = 0; float* D = nullptr; int64_t* I = nullptr; } deferred;
   } xchg;
   int64_t ntotal = 0;
   // options
@@ -303,6 +309,11 @@ int ensure_capacity(b2f_index* idx, Shard& S, int64_t need) {
   if (need <= S.cap) return B2F_OK;
   CU_TRY(cudaSetDevice(S.dev));
   int64_t ncap = std::max<int64_t>(need, S.cap + S.cap / 2);
+  if (S.n == 0) {   // nothing to keep: release first, so that regrowing a large empty shard never holds both copies
+    dev_free(S.x32); dev_free(S.x16); dev_free(S.idmap);
+    S.cap = 0;
+    ncap = need;
+  }
   float* n32 = nullptr;
   __nv_bfloat16* n16 = nullptr;
   int64_t* nid = nullptr;
@@ -512,6 +523,7 @@ void collect_prof(b2f_index* idx, Shard& S) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, P.pool[sp.b], P.pool[sp.e]) == cudaSuccess) {
       if (sp.kind == 0) { S.stats.score_ms += ms; S.stats.score_launches += 1; }
+      else if (sp.kind == 2) S.stats.xchg_ms += ms;
       else S.stats.select_ms += ms;
     } else {
       (void)cudaGetLastError();
@@ -877,6 +889,7 @@ int run_on_shards(b2f_index* idx, const std::function<int(int)>& fn) {
 // Settle every search enqueued by b2f_search_device_async: wait for the stream, then re-run (on the
 // exact engine) the queries whose candidate lists overflowed.  Normally just the synchronisation.
 int settle_pending(b2f_index* idx) {
+  if (idx->xchg_flush) B2F_TRY(idx->xchg_flush(idx));   // a merge owed by the peer exchange joins the stream first
   if (idx->pending.empty()) return B2F_OK;
   Shard& S = idx->shards[0];
   std::vector<Pending> todo;
@@ -1232,6 +1245,8 @@ int b2f_merge_packed_device_async(b2f_index* idx, const void* parts_dev, int n_p
   return B2F_OK;
 }
 
+static int xchg_flush_deferred(b2f_index* idx);
+
 int b2f_xchg_create(b2f_index* idx, int rank, int world, int64_t max_nq, int max_k, void* handle_out) {
   if (!idx || !handle_out || world < 2 || world > kXchgMaxWorld || rank < 0 || rank >= world || max_nq < 1 ||
       max_k < 1 || max_k > B2F_MAX_K)
@@ -1244,8 +1259,8 @@ int b2f_xchg_create(b2f_index* idx, int rank, int world, int64_t max_nq, int max
   auto& X = idx->xchg;
   X.rank = rank; X.world = world; X.max_nq = max_nq; X.max_k = max_k;
   X.part_cap = static_cast<size_t>(round_up(round_up(max_nq * max_k * 4, 16) + max_nq * max_k * 8, 128));
-  X.flags_off = 2 * static_cast<size_t>(world) * X.part_cap;
-  X.bytes = X.flags_off + 2 * static_cast<size_t>(world) * sizeof(unsigned int);
+  X.flags_off = kXchgSlots * static_cast<size_t>(world) * X.part_cap;
+  X.bytes = X.flags_off + kXchgSlots * static_cast<size_t>(world) * sizeof(unsigned int);
   CU_TRY(cudaMalloc(reinterpret_cast<void**>(&X.local), X.bytes));
   CU_TRY(cudaMalloc(reinterpret_cast<void**>(&X.stage), X.part_cap));
   CU_TRY(cudaMalloc(reinterpret_cast<void**>(&X.counter), sizeof(int)));
@@ -1272,32 +1287,59 @@ int b2f_xchg_connect(b2f_index* idx, const void* handles) {
     X.peer[r] = static_cast<char*>(p);
   }
   X.connected = true;
+  idx->xchg_flush = &xchg_flush_deferred;
   return B2F_OK;
 }
 
-// push the staged local part to every rank and merge what every rank pushed (both asynchronous)
+// enqueue the wait + merge of one exchange step on the index stream
+static int xchg_launch_merge(b2f_index* idx, unsigned int seq, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+  auto& X = idx->xchg;
+  Shard& S = idx->shards[0];
+  const int slot = static_cast<int>(seq % kXchgSlots);
+  const int64_t i_off = round_up(nq * k * 4, 16);
+  {
+    ProfScope ps(idx, S, 2);
+    xchg_merge_kernel<<<static_cast<int>(nq), 256, 0, S.stream>>>(
+        X.local + static_cast<size_t>(slot) * X.world * X.part_cap,
+        reinterpret_cast<const unsigned int*>(X.local + X.flags_off) + slot * X.world, seq, X.world,
+        static_cast<int64_t>(X.part_cap), i_off, nq, k, D_dev, I_dev, idx->merge_flag_dev, idx->merge_flag_dev + 1);
+  }
+  CU_TRY(cudaGetLastError());
+  idx->stats.launches += 1;
+  return B2F_OK;
+}
+
+// the merge of the previous exchange step, if it is still owed
+static int xchg_flush_deferred(b2f_index* idx) {
+  auto& X = idx->xchg;
+  if (!X.deferred.valid) return B2F_OK;
+  X.deferred.valid = false;
+  CU_TRY(cudaSetDevice(idx->shards[0].dev));
+  return xchg_launch_merge(idx, X.deferred.seq, X.deferred.nq, X.deferred.k, X.deferred.D, X.deferred.I);
+}
+
+// push the staged local part to every rank; merge what every rank pushed (now, or one step later)
 static int xchg_push_and_merge(b2f_index* idx, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
   auto& X = idx->xchg;
   Shard& S = idx->shards[0];
   const unsigned int seq = ++X.seq;
-  const int par = static_cast<int>(seq & 1u);
+  const int slot = static_cast<int>(seq % kXchgSlots);
   XchgPeers peers;
   peers.world = X.world;
   for (int r = 0; r < X.world; ++r) {
-    peers.part[r] = X.peer[r] + (static_cast<size_t>(par) * X.world + X.rank) * X.part_cap;
-    peers.flag[r] = reinterpret_cast<unsigned int*>(X.peer[r] + X.flags_off) + par * X.world + X.rank;
+    peers.part[r] = X.peer[r] + (static_cast<size_t>(slot) * X.world + X.rank) * X.part_cap;
+    peers.flag[r] = reinterpret_cast<unsigned int*>(X.peer[r] + X.flags_off) + slot * X.world + X.rank;
   }
   const int64_t i_off = round_up(nq * k * 4, 16);
   const int64_t n_vec = (i_off + nq * k * 8 + 15) / 16;
   xchg_push_kernel<<<dim3(X.world, 4), 256, 0, S.stream>>>(reinterpret_cast<const uint4*>(X.stage), n_vec, peers, seq,
                                                            X.counter);
   CU_TRY(cudaGetLastError());
-  xchg_merge_kernel<<<static_cast<int>(nq), 256, 0, S.stream>>>(
-      X.local + static_cast<size_t>(par) * X.world * X.part_cap,
-      reinterpret_cast<const unsigned int*>(X.local + X.flags_off) + par * X.world, seq, X.world,
-      static_cast<int64_t>(X.part_cap), i_off, nq, k, D_dev, I_dev, idx->merge_flag_dev, idx->merge_flag_dev + 1);
-  CU_TRY(cudaGetLastError());
-  idx->stats.launches += 2;
+  idx->stats.launches += 1;
+  if (!X.defer) return xchg_launch_merge(idx, seq, nq, k, D_dev, I_dev);
+  B2F_TRY(xchg_flush_deferred(idx));          // step seq-1: its parts arrived a whole search ago
+  X.deferred.valid = true;
+  X.deferred.seq = seq; X.deferred.nq = nq; X.deferred.k = k; X.deferred.D = D_dev; X.deferred.I = I_dev;
   return B2F_OK;
 }
 
@@ -1429,6 +1471,8 @@ int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
     idx->tighten = static_cast<int>(value);
   } else if (k == "tighten_adaptive") {
     idx->tighten_adaptive = value ? 1 : 0;
+  } else if (k == "xchg_defer") {
+    idx->xchg.defer = value ? 1 : 0;
   } else if (k == "bootstrap") {
     idx->bootstrap = value ? 1 : 0;
   } else if (k == "worst_case_margin") {
@@ -1452,6 +1496,7 @@ int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
     s.launches += S.stats.launches; s.phases += S.stats.phases; s.candidates += S.stats.candidates;
     s.fallback_queries += S.stats.fallback_queries; s.passes += S.stats.passes; s.score_ms += S.stats.score_ms;
     s.score_launches += S.stats.score_launches; s.score_rows += S.stats.score_rows; s.select_ms += S.stats.select_ms;
+    s.xchg_ms += S.stats.xchg_ms;
   }
   if (!idx->shards.empty()) {
     s.path = idx->shards[0].stats.path;
@@ -1468,6 +1513,7 @@ int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
   else if (k == "score_launches") *out = s.score_launches;
   else if (k == "score_rows") *out = s.score_rows;
   else if (k == "select_ms") *out = s.select_ms;
+  else if (k == "xchg_ms") *out = s.xchg_ms;
   else if (k == "xchg_timeout") {
     *out = idx->merge_flag_host ? static_cast<double>(idx->merge_flag_host[1]) : 0.0;
   }

@@ -706,18 +706,21 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* Dp, const int64
 // ---------------------------------------------------------------------------------------------
 // Peer-memory exchange of the one-process-per-GPU layout (replaces ncclAllGather + merge).
 //
-// Every rank owns an exchange buffer  [2 parities][world parts][part_cap bytes] + flags[2][world]
+// Every rank owns an exchange buffer  [4 slots][world parts][part_cap bytes] + flags[4][world]
 // that all peers have mapped (CUDA IPC, NVLink).  Step `seq` (parity seq & 1):
 //   xchg_push_kernel : copies this rank's packed [D | I] part into slot `rank` of EVERY rank's buffer
 //                      with 16-byte stores over NVLink; the last block to finish publishes
 //                      flags[parity][rank] = seq on every rank (fence.sys + release store);
 //   xchg_merge_kernel: waits until the `world` flags of its own buffer reach seq (acquire loads),
 //                      then merges the parts exactly like merge_kernel.
-// No host round trip, no NCCL kernel, no proxy thread.  Reuse of a parity two steps later is safe:
-// a rank's merge of step s+1 cannot complete before every peer pushed step s+1, which each peer
-// enqueues after its own merge of step s.
+// No host round trip, no NCCL kernel, no proxy thread.  The merge of step s is enqueued behind the push
+// of step s+1 (deferred by one search; b2f_search_finish flushes the last one), so a rank never idles
+// waiting for the momentarily slowest GPU.  Slot reuse four steps later is safe: a rank pushes step
+// s+4 only after its merge of step s+2, which needs every peer's push of s+2, which each peer enqueues
+// after its own merge of step s.
 // ---------------------------------------------------------------------------------------------
 constexpr int kXchgMaxWorld = 16;
+constexpr int kXchgSlots = 4;       // exchange steps in flight per rank (deferred merge needs >= 3)
 struct XchgPeers {
   char* part[kXchgMaxWorld];        // peer r: address of slot [parity][my rank] in r's buffer
   unsigned int* flag[kXchgMaxWorld];  // peer r: address of flags[parity][my rank] in r's buffer

@@ -17,9 +17,30 @@ import torch
 import torch.distributed as dist
 
 
-def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous split, identical to b2f_add's per-device split (FAISS shard=True, successive ids)."""
-    return n_total * rank // world, n_total * (rank + 1) // world
+def shard_range(n_total: int, rank: int, world: int, weights=None) -> tuple[int, int]:
+    """Contiguous split, identical to b2f_add's per-device split (FAISS shard=True, successive ids).
+    `weights` (one positive number per rank, same on every rank) makes the split proportional to them:
+    every search waits for the slowest GPU, and the B200s of one box differ by several percent under
+    the power cap, so a rank's share can follow its measured speed (`balance_weights`)."""
+    if weights is None:
+        return n_total * rank // world, n_total * (rank + 1) // world
+    assert len(weights) == world and all(w > 0 for w in weights)
+    total = float(sum(weights))
+    cuts = [0]
+    acc = 0.0
+    for w in weights:
+        acc += w
+        cuts.append(int(round(n_total * acc / total)))
+    cuts[-1] = n_total
+    return cuts[rank], cuts[rank + 1]
+
+
+def balance_weights(times, clamp: float = 0.15):
+    """Shares proportional to 1/time, limited to +-clamp around the equal share (a noisy calibration
+    must not unbalance the shards)."""
+    inv = [1.0 / max(t, 1e-9) for t in times]
+    mean = sum(inv) / len(inv)
+    return [min(max(v / mean, 1.0 - clamp), 1.0 + clamp) for v in inv]
 
 
 class ShardedFlatIP:
@@ -41,15 +62,45 @@ class ShardedFlatIP:
         self.ntotal = 0
 
     # -- building -------------------------------------------------------------------------------
-    def add_synthetic(self, n_total: int, seed: int = 0, stream: int = 0, norm: float = 1.0, chunk: int = 1 << 22):
+    def add_synthetic(self, n_total: int, seed: int = 0, stream: int = 0, norm: float = 1.0, chunk: int = 1 << 22,
+                      weights=None):
         """Every rank generates its own slice of the synthetic stream on its GPU; ids are global rows."""
-        lo, hi = shard_range(n_total, self.rank, self.world)
+        lo, hi = shard_range(n_total, self.rank, self.world, weights)
         self.index.reserve(hi - lo)
         for a in range(lo, hi, chunk):
             b = min(hi, a + chunk)
             self.index.add_synthetic(b - a, first_row=a, seed=seed, stream=stream, norm=norm, id_base=a)
         self.ntotal += n_total
         return lo, hi
+
+    def reset(self):
+        self.index.reset()
+        self.ntotal = 0
+
+    def local_seconds_per_search(self, q: torch.Tensor, k: int, reps: int = 8) -> float:
+        """Device time of this rank's LOCAL search (no exchange), for speed-weighted sharding."""
+        D = torch.empty((q.shape[0], k), dtype=torch.float32, device=q.device)
+        I = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+        ext = torch.cuda.ExternalStream(self.index.stream_ptr(0), device=q.device)
+        for _ in range(2):
+            self.index.search_device_async(q, k, D, I)
+        self.index.finish()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(reps):
+            self.index.search_device_async(q, k, D, I)
+        self.index.finish()
+        e1.record(ext)
+        torch.cuda.synchronize(q.device)
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    def gather_floats(self, value: float):
+        """The same scalar from every rank, in rank order (small control-plane exchange)."""
+        if self.world == 1:
+            return [float(value)]
+        out = [None] * self.world
+        dist.all_gather_object(out, float(value), group=self.group)
+        return out
 
     def add(self, x_global):
         """Every rank holds the same host array and keeps its slice (labels = global positions)."""

@@ -129,3 +129,17 @@ def test_sharded_search_over_gloo_world2_equals_single_index(world):
             z = np.load(os.path.join(tmp, f"rank{r}.npz"))
             np.testing.assert_array_equal(z["I"], I_ref)
             np.testing.assert_allclose(z["D"], D_ref, rtol=1e-6)
+
+
+def test_weighted_shard_ranges_partition_exactly_and_follow_the_speeds():
+    from convdr_b200.dist import balance_weights
+    times = [1.00, 1.08, 0.95, 1.02, 1.40, 1.00, 0.97, 1.01]       # one straggler far outside the clamp
+    w = balance_weights(times)
+    assert min(w) >= 0.85 - 1e-12 and max(w) <= 1.15 + 1e-12
+    n = 38_636_520
+    cuts = [shard_range(n, r, 8, w) for r in range(8)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == n
+    assert all(cuts[r][1] == cuts[r + 1][0] for r in range(7))
+    sizes = [b - a for a, b in cuts]
+    assert sizes[2] > sizes[0] > sizes[1] > sizes[4]                  # faster GPUs hold more rows
+    assert [shard_range(1001, r, 4, None) for r in range(4)] == [shard_range(1001, r, 4) for r in range(4)]
