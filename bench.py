@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--tighten", type=int, default=-1, help="-1 engine default, 0 off, >0 refresher pause in ns")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: result exchange through the engine's peer-memory kernels (default) or ncclAllGather")
-    ap.add_argument("--balance", type=int, default=1,
+    ap.add_argument("--balance", type=int, default=0,
                     help="N > 1: 1 = size each rank's shard by its measured local search speed (calibrated before "
                          "the timed region), 0 = equal shards")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (A/B experiments)")

@@ -1358,6 +1358,11 @@ int b2f_search_xchg_async(b2f_index* idx, const float* q_dev, int64_t nq, int k,
   return xchg_push_and_merge(idx, nq, k, D_dev, I_dev);
 }
 
+int b2f_xchg_flush(b2f_index* idx) {
+  if (!idx) return fail(B2F_ERR_INVALID, "null index");
+  return xchg_flush_deferred(idx);
+}
+
 int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_host, int64_t* I_host) {
   B2F_TRY(check_args_search(idx, q_host, nq, k, D_host, I_host));
   if (nq == 0) return B2F_OK;

@@ -239,9 +239,48 @@ class ShardedFlatIP:
         return D, I
 
     def search_host(self, q_host, k: int, device=None):
-        """End-to-end call with host buffers: pinned H2D of the queries, search, D2H of the result."""
-        qt = torch.from_numpy(q_host)
-        if device is not None:
-            qt = qt.pin_memory().to(device, non_blocking=True)
-        D, I = self.search(qt, k)
-        return D.cpu().numpy(), I.cpu().numpy()
+        """End-to-end call with host buffers: pinned H2D of the queries, search, D2H of the result.
+        GPU ranks: upload, search, exchange, merge and download are all queued on the engine's stream
+        (persistent pinned staging buffers), ONE host wait."""
+        if device is None or self.index is None:
+            D, I = self.search(torch.from_numpy(q_host), k)
+            return D.cpu().numpy(), I.cpu().numpy()
+        nq = q_host.shape[0]
+        key = (nq, k, str(device))
+        if getattr(self, "_hkey", None) != key:
+            self._hq = torch.empty((nq, q_host.shape[1]), dtype=torch.float32).pin_memory()
+            self._hD = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+            self._hI = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+            self._dq = torch.empty((nq, q_host.shape[1]), dtype=torch.float32, device=device)
+            self._dD = torch.empty((nq, k), dtype=torch.float32, device=device)
+            self._dI = torch.empty((nq, k), dtype=torch.int64, device=device)
+            self._hkey = key
+        if getattr(self, "_ext", None) is None:
+            self._ext = torch.cuda.ExternalStream(self.index.stream_ptr(0), device=device)
+        self._hq.numpy()[...] = q_host
+        with torch.cuda.stream(self._ext):
+            self._dq.copy_(self._hq, non_blocking=True)
+
+        def download():
+            if self.world > 1 and getattr(self, "_last_peer", False):
+                self.index.xchg_flush()              # the deferred merge joins the stream now, no wait
+            with torch.cuda.stream(self._ext):
+                self._hD.copy_(self._dD, non_blocking=True)
+                self._hI.copy_(self._dI, non_blocking=True)
+
+        self.search_async(self._dq, k, self._dD, self._dI)
+        download()
+        self.index.finish()                          # the one host wait (also settles overflowed queries)
+        redo = self.world > 1 and self.index.stat("merge_saw_overflow") > 0
+        fb = self.index.stat("fallback_queries")          # cumulative over asynchronous searches
+        if fb != getattr(self, "_fb_seen", 0.0) or redo:
+            # rare: a list overflowed.  The local rows were re-run by finish(); repeat exchange / download.
+            self._fb_seen = fb
+            if self.world > 1:
+                D, I = self._search_cuda(self._dq, k)
+                self._dD.copy_(D); self._dI.copy_(I)
+                self._ext.wait_stream(torch.cuda.current_stream(device))
+                self._fb_seen = self.index.stat("fallback_queries")
+            download()
+            self.index.finish()
+        return self._hD.numpy().copy(), self._hI.numpy().copy()

@@ -186,6 +186,10 @@ class FlatIPIndex:
         _lib.check(_lib.load().b2f_search_xchg_async(self._ensure(), q.data_ptr(), q.shape[0], int(k), D.data_ptr(),
                                                      I.data_ptr(), 1 if repush_only else 0))
 
+    def xchg_flush(self) -> None:
+        """Enqueue the exchange merge that is still owed (deferred by one search), without waiting."""
+        _lib.check(_lib.load().b2f_xchg_flush(self._ensure()))
+
     def reset_stats(self) -> None:
         self.set_option("reset_stats", 1)
 

@@ -149,6 +149,12 @@ int b2f_xchg_create(b2f_index* idx, int rank, int world, int64_t max_nq, int max
 int b2f_xchg_connect(b2f_index* idx, const void* handles);
 int b2f_search_xchg_async(b2f_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
                           int64_t* I_dev, int repush_only);
+/* The merge of an exchange step is enqueued one search later (the ranks are then
+ * coupled with one step of slack instead of a barrier per search; option
+ * "xchg_defer", default 1) or by b2f_search_finish.  b2f_xchg_flush enqueues a
+ * merge that is still owed WITHOUT waiting, so that a caller can queue its own
+ * work (a download of D_dev / I_dev) behind it before the one host wait.        */
+int b2f_xchg_flush(b2f_index* idx);
 
 /* faiss IndexFlat.reconstruct_n(i0, ni): copy stored rows [row0, row0+n) of shard
  * `shard` (shard-local positions) back to host memory — inspection / tests.    */
