@@ -57,6 +57,13 @@ def main():
         for D, I in outs:
             np.testing.assert_array_equal(I.cpu().numpy(), If)
             np.testing.assert_array_equal(D.cpu().numpy(), Df)
+        # host-buffer path (one host wait; the 173-query batch contains two overflowing queries -> redo branch)
+        for nq, kk, seed in ((37, 100, 2), (173, 100, 3), (37, 100, 2)):
+            qh = synth.block(0, nq, seed=seed, stream=1)
+            Dh, Ih = sh.search_host(qh, kk, device=dev)
+            Df, If = full.search(qh, kk)
+            np.testing.assert_array_equal(Ih, If)
+            np.testing.assert_array_equal(Dh, Df)
         results[mode] = out
     for (Da, Ia), (Db, Ib) in zip(results["nccl"], results["peer"]):
         np.testing.assert_array_equal(Ia, Ib)
