@@ -973,6 +973,12 @@ int b2f_create(int d, const int* devices, int n_dev, b2f_index** out) {
       b2f_destroy(idx);
       return fail(B2F_ERR_CUDA, m);
     }
+    if (cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeStageMaxBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeStageMaxBytes) != cudaSuccess) {
+      (void)cudaGetLastError();
+      b2f_destroy(idx);
+      return fail(B2F_ERR_CUDA, "cannot reserve shared memory for the merge kernels");
+    }
     S.sm_count = prop.multiProcessorCount;
     S.max_pairs = std::min(128, std::max(1, S.sm_count / 2));
   }
@@ -1220,8 +1226,9 @@ int b2f_merge_device(b2f_index* idx, const float* D_parts_dev, const int64_t* I_
   if (nq == 0) return B2F_OK;
   Shard& S = idx->shards[0];
   CU_TRY(cudaSetDevice(S.dev));
-  merge_kernel<<<static_cast<int>(nq), 256, 0, S.stream>>>(D_parts_dev, I_parts_dev, n_parts, nq, k, D_dev, I_dev,
-                                                           nq * k, nq * k, nullptr);
+  const int msb = merge_stage_bytes(n_parts, k);
+  merge_kernel<<<static_cast<int>(nq), 256, msb, S.stream>>>(D_parts_dev, I_parts_dev, n_parts, nq, k, D_dev, I_dev,
+                                                             nq * k, nq * k, nullptr, msb > 0);
   CU_TRY(cudaGetLastError());
   idx->stats.launches += 1;
   CU_TRY(cudaStreamSynchronize(S.stream));
@@ -1237,9 +1244,10 @@ int b2f_merge_packed_device_async(b2f_index* idx, const void* parts_dev, int n_p
   Shard& S = idx->shards[0];
   CU_TRY(cudaSetDevice(S.dev));
   const char* base = static_cast<const char*>(parts_dev);
-  merge_kernel<<<static_cast<int>(nq), 256, 0, S.stream>>>(
+  const int msb = merge_stage_bytes(n_parts, k);
+  merge_kernel<<<static_cast<int>(nq), 256, msb, S.stream>>>(
       reinterpret_cast<const float*>(base), reinterpret_cast<const int64_t*>(base + i_offset_bytes), n_parts, nq, k,
-      D_dev, I_dev, part_bytes / 4, part_bytes / 8, idx->merge_flag_dev);
+      D_dev, I_dev, part_bytes / 4, part_bytes / 8, idx->merge_flag_dev, msb > 0);
   CU_TRY(cudaGetLastError());
   idx->stats.launches += 1;
   return B2F_OK;
@@ -1299,10 +1307,12 @@ static int xchg_launch_merge(b2f_index* idx, unsigned int seq, int64_t nq, int k
   const int64_t i_off = round_up(nq * k * 4, 16);
   {
     ProfScope ps(idx, S, 2);
-    xchg_merge_kernel<<<static_cast<int>(nq), 256, 0, S.stream>>>(
+    const int msb = merge_stage_bytes(X.world, k);
+    xchg_merge_kernel<<<static_cast<int>(nq), 256, msb, S.stream>>>(
         X.local + static_cast<size_t>(slot) * X.world * X.part_cap,
         reinterpret_cast<const unsigned int*>(X.local + X.flags_off) + slot * X.world, seq, X.world,
-        static_cast<int64_t>(X.part_cap), i_off, nq, k, D_dev, I_dev, idx->merge_flag_dev, idx->merge_flag_dev + 1);
+        static_cast<int64_t>(X.part_cap), i_off, nq, k, D_dev, I_dev, idx->merge_flag_dev, idx->merge_flag_dev + 1,
+        msb > 0);
   }
   CU_TRY(cudaGetLastError());
   idx->stats.launches += 1;
@@ -1429,7 +1439,9 @@ int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_
     CU_TRY(cudaMemcpyPeerAsync(W.Dp + per * g, S0.dev, S.ws.D, S.dev, sizeof(float) * per, S0.stream));
     CU_TRY(cudaMemcpyPeerAsync(W.Ip + per * g, S0.dev, S.ws.I, S.dev, sizeof(int64_t) * per, S0.stream));
   }
-  merge_kernel<<<static_cast<int>(nq), 256, 0, S0.stream>>>(W.Dp, W.Ip, G, nq, k, W.Dp + per * G, W.Ip + per * G, per, per, nullptr);
+  const int msb = merge_stage_bytes(G, k);
+  merge_kernel<<<static_cast<int>(nq), 256, msb, S0.stream>>>(W.Dp, W.Ip, G, nq, k, W.Dp + per * G, W.Ip + per * G, per, per,
+                                                              nullptr, msb > 0);
   CU_TRY(cudaGetLastError());
   idx->stats.launches += 1;
   const float* Dres = W.Dp + per * G;

@@ -652,32 +652,47 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
 // Part g starts at Dp + g*strideD floats / Ip + g*strideI int64s (nq*k for two dense arrays; the
 // packed [D | I] records of the exchange use the packed part size).  Parts are read with ld.global.cg:
 // in the peer-memory exchange they are written by OTHER GPUs while this kernel is already resident.
+// The G lists of the query are first staged in shared memory (G*k*12 bytes; `staged` = 0 when that does
+// not fit): the G-1 binary searches per element would otherwise be ~100 dependent L2 round trips per
+// thread (measured 0.15-0.25 ms per merge at G = 8 before staging).
 __device__ __forceinline__ void merge_body(const float* Dp, const int64_t* Ip, int G, int64_t q,
                                            int k, float* __restrict__ D, int64_t* __restrict__ I,
-                                           int64_t strideD, int64_t strideI, int* saw_overflow, int* total_valid_s) {
-  if (threadIdx.x == 0) *total_valid_s = 0;
-  __syncthreads();
+                                           int64_t strideD, int64_t strideI, int* saw_overflow, int* total_valid_s,
+                                           int staged, unsigned char* stage_smem) {
   const int E = G * k;
+  int64_t* sI = reinterpret_cast<int64_t*>(stage_smem);            // [G][k]
+  float* sD = reinterpret_cast<float*>(stage_smem + static_cast<size_t>(E) * sizeof(int64_t));   // [G][k]
+  if (threadIdx.x == 0) *total_valid_s = 0;
+  if (staged) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const int g = e / k, i = e - g * k;
+      sI[e] = __ldcg(Ip + static_cast<int64_t>(g) * strideI + q * k + i);
+      sD[e] = __ldcg(Dp + static_cast<int64_t>(g) * strideD + q * k + i);
+    }
+  }
+  __syncthreads();
+  auto ld_id = [&](int g, int i) -> int64_t {
+    return staged ? sI[g * k + i] : __ldcg(Ip + static_cast<int64_t>(g) * strideI + q * k + i);
+  };
+  auto ld_score = [&](int g, int i) -> float {
+    return staged ? sD[g * k + i] : __ldcg(Dp + static_cast<int64_t>(g) * strideD + q * k + i);
+  };
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     const int g = e / k, i = e - g * k;
-    const int64_t baseD = static_cast<int64_t>(g) * strideD + q * k;
-    const int64_t baseI = static_cast<int64_t>(g) * strideI + q * k;
-    const int64_t id = __ldcg(Ip + baseI + i);
+    const int64_t id = ld_id(g, i);
     if (id == -2 && saw_overflow != nullptr) *saw_overflow = 1;   // a shard's list overflowed: result pending its re-run
     if (id < 0) continue;
     atomicAdd(total_valid_s, 1);
-    const float s = __ldcg(Dp + baseD + i);
+    const float s = ld_score(g, i);
     int rank = i;
     for (int g2 = 0; g2 < G; ++g2) {
       if (g2 == g) continue;
-      const int64_t b2D = static_cast<int64_t>(g2) * strideD + q * k;
-      const int64_t b2I = static_cast<int64_t>(g2) * strideI + q * k;
       // count valid elements of list g2 that precede (s): score > s, or == s when g2 < g
       int lo = 0, hi = k;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const bool valid = __ldcg(Ip + b2I + mid) >= 0;
-        const float s2 = __ldcg(Dp + b2D + mid);
+        const bool valid = ld_id(g2, mid) >= 0;
+        const float s2 = ld_score(g2, mid);
         const bool before = valid && (s2 > s || (s2 == s && g2 < g));
         if (before) lo = mid + 1; else hi = mid;
       }
@@ -695,12 +710,20 @@ __device__ __forceinline__ void merge_body(const float* Dp, const int64_t* Ip, i
   }
 }
 
+constexpr int kMergeStageMaxBytes = 96 * 1024;
+inline int merge_stage_bytes(int G, int k) {   // dynamic shared memory of the merge kernels (0: lists stay in L2)
+  const int64_t b = static_cast<int64_t>(G) * k * 12;
+  return b <= kMergeStageMaxBytes ? static_cast<int>(b) : 0;
+}
+
 __global__ void __launch_bounds__(256) merge_kernel(const float* Dp, const int64_t* Ip, int G, int64_t nq,
                                                     int k, float* __restrict__ D, int64_t* __restrict__ I,
                                                     int64_t strideD, int64_t strideI,
-                                                    int* __restrict__ saw_overflow /* mapped host int or null */) {
+                                                    int* __restrict__ saw_overflow /* mapped host int or null */,
+                                                    int staged) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
   __shared__ int total_valid;
-  merge_body(Dp, Ip, G, blockIdx.x, k, D, I, strideD, strideI, saw_overflow, &total_valid);
+  merge_body(Dp, Ip, G, blockIdx.x, k, D, I, strideD, strideI, saw_overflow, &total_valid, staged, merge_smem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -751,7 +774,8 @@ __global__ void __launch_bounds__(256) xchg_merge_kernel(const char* __restrict_
                                                          const unsigned int* flags /* [world] of this parity */,
                                                          unsigned int seq, int world, int64_t part_cap, int64_t i_off,
                                                          int64_t nq, int k, float* __restrict__ D, int64_t* __restrict__ I,
-                                                         int* __restrict__ saw_overflow, int* __restrict__ err) {
+                                                         int* __restrict__ saw_overflow, int* __restrict__ err, int staged) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
   __shared__ int total_valid;
   if (threadIdx.x < world) {
     long long t0 = 0;
@@ -769,7 +793,7 @@ __global__ void __launch_bounds__(256) xchg_merge_kernel(const char* __restrict_
   }
   __syncthreads();
   merge_body(reinterpret_cast<const float*>(parts), reinterpret_cast<const int64_t*>(parts + i_off), world, blockIdx.x, k,
-             D, I, part_cap / 4, part_cap / 8, saw_overflow, &total_valid);
+             D, I, part_cap / 4, part_cap / 8, saw_overflow, &total_valid, staged, merge_smem);
 }
 
 }  // namespace b2f

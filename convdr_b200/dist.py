@@ -181,22 +181,19 @@ class ShardedFlatIP:
         in stream order."""
         nq = q.shape[0]
         idx = self.index
+        if getattr(self, "_ext", None) is None:
+            self._ext = torch.cuda.ExternalStream(idx.stream_ptr(0), device=q.device)
+        self._ext.wait_stream(torch.cuda.current_stream(q.device))     # q may have been produced there
         if self.world == 1:
             idx.search_device_async(q, k, D, I)
             return
         if getattr(self, "_peer", False) and nq * k <= self._peer_cap[0] * self._peer_cap[1] and nq <= self._peer_cap[0] \
                 and k <= self._peer_cap[1]:
-            if getattr(self, "_ext", None) is None:
-                self._ext = torch.cuda.ExternalStream(idx.stream_ptr(0), device=q.device)
-            self._ext.wait_stream(torch.cuda.current_stream(q.device))
             idx.search_xchg_async(q, k, D, I)     # search -> NVLink push -> wait + merge, all engine kernels
             self._last_peer = True
             return
         self._last_peer = False
         send, recv = self._buffers(nq, k, q.device)
-        if getattr(self, "_ext", None) is None:
-            self._ext = torch.cuda.ExternalStream(idx.stream_ptr(0), device=q.device)
-        self._ext.wait_stream(torch.cuda.current_stream(q.device))     # q may have been produced there
         with torch.cuda.stream(self._ext):
             idx.search_device_async(q, k, self._Dl, self._Il)          # local top-k with global ids
             dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)  # the only exchange (NCCL)
@@ -257,20 +254,24 @@ class ShardedFlatIP:
             self._hkey = key
         if getattr(self, "_ext", None) is None:
             self._ext = torch.cuda.ExternalStream(self.index.stream_ptr(0), device=device)
+        cur = torch.cuda.current_stream(device)
+        # The pinned staging tensors only ever meet torch's own stream (its host allocator records the
+        # streams a pinned block was used on and touches them again when the block is freed, possibly
+        # after the engine's stream is gone); the engine stream is ordered against it with events.
         self._hq.numpy()[...] = q_host
-        with torch.cuda.stream(self._ext):
-            self._dq.copy_(self._hq, non_blocking=True)
+        self._dq.copy_(self._hq, non_blocking=True)
 
         def download():
             if self.world > 1 and getattr(self, "_last_peer", False):
-                self.index.xchg_flush()              # the deferred merge joins the stream now, no wait
-            with torch.cuda.stream(self._ext):
-                self._hD.copy_(self._dD, non_blocking=True)
-                self._hI.copy_(self._dI, non_blocking=True)
+                self.index.xchg_flush()              # the deferred merge joins the engine stream now, no wait
+            cur.wait_stream(self._ext)
+            self._hD.copy_(self._dD, non_blocking=True)
+            self._hI.copy_(self._dI, non_blocking=True)
+            cur.synchronize()                        # the one host wait: upload, search, exchange, merge, download
+            self.index.finish()                      # stream already idle: settles the overflow flags
 
-        self.search_async(self._dq, k, self._dD, self._dI)
+        self.search_async(self._dq, k, self._dD, self._dI)   # waits (on device) for the upload
         download()
-        self.index.finish()                          # the one host wait (also settles overflowed queries)
         redo = self.world > 1 and self.index.stat("merge_saw_overflow") > 0
         fb = self.index.stat("fallback_queries")          # cumulative over asynchronous searches
         if fb != getattr(self, "_fb_seen", 0.0) or redo:
@@ -279,8 +280,6 @@ class ShardedFlatIP:
             if self.world > 1:
                 D, I = self._search_cuda(self._dq, k)
                 self._dD.copy_(D); self._dI.copy_(I)
-                self._ext.wait_stream(torch.cuda.current_stream(device))
                 self._fb_seen = self.index.stat("fallback_queries")
             download()
-            self.index.finish()
         return self._hD.numpy().copy(), self._hI.numpy().copy()
