@@ -272,14 +272,17 @@ class ShardedFlatIP:
 
         self.search_async(self._dq, k, self._dD, self._dI)   # waits (on device) for the upload
         download()
-        redo = self.world > 1 and self.index.stat("merge_saw_overflow") > 0
-        fb = self.index.stat("fallback_queries")          # cumulative over asynchronous searches
-        if fb != getattr(self, "_fb_seen", 0.0) or redo:
-            # rare: a list overflowed.  The local rows were re-run by finish(); repeat exchange / download.
-            self._fb_seen = fb
-            if self.world > 1:
+        # Rare: a candidate list overflowed; finish() re-ran those queries locally.  With several ranks the
+        # decision to repeat the exchange must be the same everywhere, so it only looks at the in-band
+        # marker every rank's merge saw (never at a rank-local counter).
+        if self.world > 1:
+            if self.index.stat("merge_saw_overflow") > 0:
                 D, I = self._search_cuda(self._dq, k)
                 self._dD.copy_(D); self._dI.copy_(I)
-                self._fb_seen = self.index.stat("fallback_queries")
-            download()
+                download()
+        else:
+            fb = self.index.stat("fallback_queries")      # cumulative over asynchronous searches
+            if fb != getattr(self, "_fb_seen", 0.0):
+                self._fb_seen = fb
+                download()
         return self._hD.numpy().copy(), self._hI.numpy().copy()
