@@ -468,3 +468,19 @@ def test_shard_with_a_block_of_identical_rows_overflows_for_some_queries_only():
     Dr, Ir = ref.search(Qh, 100)
     np.testing.assert_array_equal(I.cpu().numpy(), Ir)
     np.testing.assert_array_equal(D.cpu().numpy(), Dr)
+
+
+@pytest.mark.parametrize("opts", [dict(bootstrap=1), dict(tighten_adaptive=0, tighten=400), dict(worst_case_margin=1),
+                                  dict(bootstrap=1, tighten=0)])
+def test_schedule_options_of_the_tensor_engine_give_identical_results(opts, c1_data):
+    """Every schedule of the TS engine (no bootstrap / dense bootstrap launch, adaptive / fixed refresher
+    pacing, data-dependent / worst-case margin, geometric phases) returns the same bits: the schedule only
+    decides how many candidates are looked at, the exact rescoring decides the result."""
+    P, Q = c1_data
+    base = make_index("umma_ts", P)
+    D0, I0 = base.search(Q, 100)
+    var = make_index("umma_ts", P, **opts)
+    D1, I1 = var.search(Q, 100)
+    np.testing.assert_array_equal(I1, I0)
+    np.testing.assert_array_equal(D1, D0)
+    assert var.stat("fallback_queries") == 0
