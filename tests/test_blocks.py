@@ -112,3 +112,25 @@ def test_convert_and_chunked_load_feed_every_row_once(tmp_path):
     Do, Io = flat_ip.search_one_by_one(str(tmp_path), ref, Q, 10)
     np.testing.assert_array_equal(Ir, Io[:, :10])
     np.testing.assert_allclose(Dr, Do[:, :10], rtol=1e-6)
+
+
+def test_block_format_is_pinned_by_files_the_reference_writer_produced(tmp_path):
+    """tests/golden/ref_blocks/*.pb were written by the reference's own `barrier_array_merge`
+    (utils/util.py:88-143, imported with stubs by tests/golden/make_golden_blocks.py).  Our reader must
+    return the arrays that went in, our writer must produce the same file names and — under the numpy
+    that produced the fixtures — the same bytes."""
+    import json
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_blocks")
+    prm = json.load(open(os.path.join(gdir, "params.json")))
+    emb = synth.block(0, prm["n_rows"], seed=prm["seed"])
+    embid = blocks.strided_offsets(prm["n_rows"] * prm["world"], prm["rank"], prm["world"])
+    assert prm["files"] == [blocks.EMB_NAME % prm["rank"], blocks.EMBID_NAME % prm["rank"]]
+    e, i = blocks.read_block(gdir, prm["rank"])
+    np.testing.assert_array_equal(e, emb)
+    np.testing.assert_array_equal(i, embid)
+    assert e.dtype == np.float32 and i.dtype == np.int64
+    pe, pi = blocks.write_block(str(tmp_path), prm["rank"], emb, embid)
+    assert sorted(os.listdir(tmp_path)) == prm["files"]
+    if np.__version__.split(".")[:2] == prm["numpy"].split(".")[:2]:
+        assert open(pe, "rb").read() == open(os.path.join(gdir, prm["files"][0]), "rb").read()
+        assert open(pi, "rb").read() == open(os.path.join(gdir, prm["files"][1]), "rb").read()
