@@ -143,3 +143,19 @@ def test_weighted_shard_ranges_partition_exactly_and_follow_the_speeds():
     sizes = [b - a for a, b in cuts]
     assert sizes[2] > sizes[0] > sizes[1] > sizes[4]                  # faster GPUs hold more rows
     assert [shard_range(1001, r, 4, None) for r in range(4)] == [shard_range(1001, r, 4) for r in range(4)]
+
+
+def test_bench_reference_arm_prints_one_contract_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) on a tiny sample: exactly one
+    JSON line on stdout with the keys of the bench contract."""
+    import json
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cpu-sample-rows",
+                          "20000", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "queries/s" and j["higher_is_better"] is True
+    assert j["value"] > 0 and j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and "sample" in j["cpu_baseline"]
+    assert j["metric"].startswith("exact top-100 queries/sec") and j["config"]["workload"]
