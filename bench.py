@@ -51,8 +51,12 @@ def parse_args():
     ap.add_argument("--k", type=int, default=TOPK)
     ap.add_argument("--path", default="auto")
     ap.add_argument("--growth", type=int, default=0, help="phase growth factor override (0 = engine default)")
-    ap.add_argument("--variant", type=int, default=0, help="tensor engine variant: 0 auto, 1 SS, 2 TS")
-    ap.add_argument("--l2-prefetch", type=int, default=1)
+    ap.add_argument("--variant", type=int, default=0,
+                    help="tensor engine variant: 0 auto (QS up to 208 queries per pass, TS above), 1 QS with resident "
+                         "queries, 2 TS, 3 QS")
+    ap.add_argument("--data", default="iso", choices=["iso", "aniso"],
+                    help="synthetic rows: iso = isotropic unit-norm (BASELINE.json), aniso = norm 28 with a common "
+                         "mean component, cos(p,p') ~ 0.9 (LayerNorm-like ANCE embeddings)")
     ap.add_argument("--tighten", type=int, default=-1, help="-1 engine default, 0 off, >0 refresher pause in ns")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: result exchange through the engine's peer-memory kernels (default) or ncclAllGather")
@@ -80,14 +84,15 @@ def measured_peaks():
     return 6650.0, 1500.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch(rows_per_launch: float):
+def ncu_traffic_per_launch(rows_per_launch: float, kernel: str = "umma_score_select_kernel"):
     """DRAM bytes (read + write) per launch of the dominant kernel, from the committed
     `ncu --set full` capture (profiles/ncu_summary.json: bytes per row of the captured launch) scaled
     to the rows one average launch of this run streams."""
     path = os.path.join(ROOT, "profiles", "ncu_summary.json")
     try:
         with open(path) as f:
-            per_row = json.load(f)["umma_score_select_kernel"]["dram_bytes_per_row"]
+            j = json.load(f)
+            per_row = (j.get(kernel) or j["umma_score_select_kernel"])["dram_bytes_per_row"]
         return per_row * rows_per_launch
     except Exception:
         return None
@@ -302,23 +307,24 @@ def run_b2f_arm(args):
     if args.growth:
         index.set_option("growth", args.growth)
     index.set_option("umma_variant", args.variant)
-    index.set_option("l2_prefetch", args.l2_prefetch)
     if args.tighten >= 0:
         index.set_option("tighten", args.tighten)
     for kv in args.opt:
         key, val = kv.split("=")
         index.set_option(key, int(val))
+    data_norm, data_shift = (28.0, 443) if args.data == "aniso" else (1.0, 0)
+    index.set_option("synth_mean_shift", data_shift)
     sharded = ShardedFlatIP(index=index)
     exchange = "none"
     if world > 1:
         exchange = "peer-memory kernels (CUDA IPC over NVLink)" if (args.exchange == "peer" and
                    sharded.enable_peer_exchange(args.nq, args.k)) else "ncclAllGather + merge kernel"
     t0 = time.perf_counter()
-    lo, hi = sharded.add_synthetic(args.rows, seed=0, stream=0)
+    lo, hi = sharded.add_synthetic(args.rows, seed=0, stream=0, norm=data_norm)
     build_s = time.perf_counter() - t0
     n_local = hi - lo
 
-    q_host = synth.block(0, args.nq, seed=0, stream=1)
+    q_host = synth.block(0, args.nq, seed=0, stream=1, norm=data_norm, mean_shift=data_shift)
     q_pin = torch.from_numpy(q_host).pin_memory()
     q_dev = q_pin.to(dev)
     nq, k = args.nq, args.k
@@ -331,7 +337,7 @@ def run_b2f_arm(args):
         times = sharded.gather_floats(sharded.local_seconds_per_search(q_dev, k))
         weights = balance_weights(times)
         sharded.reset()
-        lo, hi = sharded.add_synthetic(args.rows, seed=0, stream=0, weights=weights)
+        lo, hi = sharded.add_synthetic(args.rows, seed=0, stream=0, norm=data_norm, weights=weights)
         n_local = hi - lo
         balance = {"calibration_ms_equal_shards": [round(t * 1e3, 4) for t in times],
                    "shares": [round(w / sum(weights), 5) for w in weights]}
@@ -379,6 +385,7 @@ def run_b2f_arm(args):
     dev_ms = ev0.elapsed_time(ev1)
     launches, score_ms, score_launches = index.stat("launches"), index.stat("score_ms"), index.stat("score_launches")
     score_rows, select_ms = index.stat("score_rows"), index.stat("select_ms")
+    passes_per_search, qs_passes = index.stat("passes") / max(args.steps, 1), index.stat("qs_passes") / max(args.steps, 1)
     fallbacks_timed = index.stat("fallback_queries")
     per_rank = None
     if world > 1:   # where every rank spent the step: local scoring, selection, waiting for + merging the parts
@@ -428,6 +435,12 @@ def run_b2f_arm(args):
         # dominant kernel: umma_score_select_kernel.  Per launch: rows streamed * 1536 B (bf16 shadow).
         ms_per_launch = sl[0] / max(sl[1], 1.0)
         rows_per_launch = sl[2] / max(sl[1], 1.0)
+        # which scoring kernel ran, and the MMA lanes it issues per passage row: QS puts the queries on the N side
+        # (batch rounded up to 16), TS always issues M = 256 query lanes
+        all_qs = qs_passes > 0 and qs_passes >= passes_per_search
+        kernel_name = "umma_qs_score_select_kernel" if all_qs else (
+            "umma_score_select_kernel" if qs_passes == 0 else "umma_score_select_kernel + umma_qs_score_select_kernel")
+        lanes_issued = (-(-min(nq, 256) // 16) * 16) if all_qs else 256
         achieved = rows_per_launch * BYTES_STREAMED_PER_ROW / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch > 0 else 0.0
         line = {
             "metric": METRIC, "value": nq * args.steps / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
@@ -438,28 +451,30 @@ def run_b2f_arm(args):
                 "workload": f"CAsT-sized {args.rows}x768 collection (BASELINE.json configs[3]), {nq} queries, top-{k}, "
                             f"row-sharded over {n_gpus} GPU(s), {n_local} rows on rank 0",
                 "l2_policy": "inputs larger than L2 (>= 7 GB streamed per GPU per step vs 126 MB L2); no flush needed",
-                "engine_path": engine_path, "tensor_variant": args.variant, "l2_prefetch": args.l2_prefetch,
+                "engine_path": engine_path, "tensor_variant": args.variant, "data": args.data,
+                "passes_per_search": passes_per_search, "qs_passes_per_search": qs_passes,
                 "build_seconds": round(build_s, 2),
                 "parallelism": f"shard{n_gpus}", "exchange": exchange, "balance": balance,
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": ncu_traffic_per_launch(rows_per_launch),
+                "frac": achieved / peak if peak else None, "traffic": ncu_traffic_per_launch(rows_per_launch, kernel_name),
                 "algorithmic_bytes_per_launch": rows_per_launch * BYTES_STREAMED_PER_ROW,
-                "peak_source": peak_src, "kernel": "umma_score_select_kernel",
+                "peak_source": peak_src, "kernel": kernel_name,
                 "bytes_per_row_streamed": BYTES_STREAMED_PER_ROW,
                 "achieved_fp32_equivalent": achieved * BYTES_ALGO_FP32_PER_ROW / BYTES_STREAMED_PER_ROW,
                 "rows_per_launch": rows_per_launch, "ms_per_launch": ms_per_launch,
                 "score_kernel_share_of_step": sl[0] / dev_ms_max if dev_ms_max else None,
                 "select_kernels_ms_per_step": sl[4] / args.steps,
                 "whole_step_streamed_gbs_per_gpu": n_local * BYTES_STREAMED_PER_ROW * args.steps / (dev_ms_max * 1e-3) / 1e9,
-                # the same kernel against the tensor roofline: a pass issues M = 256 query lanes per row
-                # whatever nq is (tcgen05 cta_group::2 M granularity), so 173 queries pay for 256
+                # the same kernel against the tensor roofline: lanes issued per passage row (TS: always 256,
+                # the cta_group::2 M granularity; QS: the batch rounded up to 16) vs the queries actually served
                 "tensor": (lambda rps, passes: {
-                    "issued_tflops": rps * 2 * 256 * D / 1e12,
+                    "lanes_issued_per_row": lanes_issued,
+                    "issued_tflops": rps * 2 * lanes_issued * D / 1e12,
                     "useful_tflops": rps * 2 * (nq / passes) * D / 1e12,
                     "peak_bf16_sustained_tflops": tensor_peak,
-                    "frac_issued": (rps * 2 * 256 * D / 1e12) / tensor_peak if tensor_peak else None,
+                    "frac_issued": (rps * 2 * lanes_issued * D / 1e12) / tensor_peak if tensor_peak else None,
                 })(rows_per_launch / (ms_per_launch * 1e-3) if ms_per_launch > 0 else 0.0, max(-(-nq // 256), 1)),
             },
             "e2e": {"value": nq * args.steps / e2e_s, "unit": UNIT,
@@ -491,7 +506,9 @@ def self_check(index, sharded, q_host, q_dev, Dd, Id, De, Ie, args, lo, hi, worl
     out["ids_in_range"] = bool(((In >= 0) & (In < args.rows)).all())
     out["host_api_equals_device_api"] = bool(np.array_equal(In, Ie) and np.array_equal(Dn, De))
     sel = [0, args.nq // 2, args.nq - 1]
-    rows = synth.rows(In[sel].reshape(-1).astype(np.uint64), seed=0, stream=0).reshape(len(sel), args.k, D)
+    data_norm, data_shift = (28.0, 443) if args.data == "aniso" else (1.0, 0)
+    rows = synth.rows(In[sel].reshape(-1).astype(np.uint64), seed=0, stream=0, norm=data_norm,
+                      mean_shift=data_shift).reshape(len(sel), args.k, D)
     s64 = np.einsum("qd,qkd->qk", q_host[sel].astype(np.float64), rows.astype(np.float64))
     rel = np.abs(Dn[sel] - s64) / np.maximum(np.abs(s64), 1e-30)
     out["max_rel_err_vs_host_fp64_rescoring"] = float(rel.max())

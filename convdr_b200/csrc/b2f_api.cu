@@ -31,7 +31,7 @@
 #include "kernels_scan.cuh"
 #include "kernels_select.cuh"
 #include "kernels_umma.cuh"
-#include "kernels_umma_ss.cuh"
+#include "kernels_umma_qs.cuh"
 #include "kernels_util.cuh"
 
 using namespace b2f;
@@ -96,7 +96,9 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint32_t c
   return B2F_OK;
 }
 
-constexpr int kMaxPending = 16;   // asynchronous device searches in flight (one overflow-flag slot each)
+constexpr int kMaxPending = 16;
+constexpr int kMuBlocks = 256;          // partial column sums of the centre
+constexpr int64_t kMuRows = 65536;      // the centre is the mean of (up to) the first 65536 rows of the first add   // asynchronous device searches in flight (one overflow-flag slot each)
 
 struct Workspace {
   // candidate state of one pass
@@ -140,7 +142,7 @@ struct Workspace {
 };
 
 struct Stats {
-  double launches = 0, phases = 0, candidates = 0, fallback_queries = 0, path = 0, passes = 0;
+  double launches = 0, phases = 0, candidates = 0, fallback_queries = 0, path = 0, passes = 0, qs_passes = 0;
   double score_ms = 0, score_launches = 0, score_rows = 0, select_ms = 0, xchg_ms = 0;
 };
 
@@ -170,7 +172,10 @@ struct Shard {
   float* x32 = nullptr;
   __nv_bfloat16* x16 = nullptr;
   int64_t n = 0, cap = 0;
-  unsigned int* maxnorm2 = nullptr;  // device, float bits: [0] max ||p||^2, [1] max ||p - bf16(p)||^2
+  unsigned int* maxnorm2 = nullptr;  // device, float bits: [0] max ||p||^2, [1] max ||(p - mu) - shadow||^2, [2] max ||p - mu||^2
+  float* mu = nullptr;               // device [768]: the shard's centre (zeros until set / when centring is off)
+  float* mu_part = nullptr;          // device [kMuBlocks][768]: partial column sums
+  bool mu_set = false;
   int64_t* idmap = nullptr;          // optional explicit labels [cap]
   bool has_ids = false;
   std::vector<Seg> segs;
@@ -269,9 +274,16 @@ struct b2f_index {
   int growth = 32;
   int64_t margin_ppm = 1000000;
   int keep_on_reset = 1;
-  int scan_max_auto = 4;  // AUTO: batches up to this size use the SIMT scan
+  int scan_max_auto = 0;  // AUTO: batches up to this size use the SIMT scan (0: the tensor engine streams half the
+                          // bytes and wins from one query on — profiles/r01s2_sweep_8p8M_*.json)
   int profile = 0;
-  int umma_variant = 0;   // 0 auto, 1 smem-stationary queries (SS), 2 TMEM-stationary queries (TS)
+  int umma_variant = 0;   // 0 auto (QS up to qs_max_q queries per pass, TS above), 1 QS with every query K-block
+                          // resident in shared memory (the round-1 "SS" layout), 2 TS (queries in TMEM), 3 QS
+  int qs_max_q = 208;     // AUTO: passes of up to this many queries take the QS variant (MMA N = nq rounded to 16)
+  int qs_resident_kb = 0; // QS: query K-blocks kept resident in shared memory (0..12); the rest streams from L2
+  int qs_q_stages = 3;    // QS: depth of the query ring
+  int center = 1;         // subtract the collection mean (first rows of the first add) before the bf16 rounding
+  int synth_mean_shift = 0;  // b2f_add_synthetic: integer shift of every component along a fixed sign vector
   int l2_prefetch = 1;
   int worst_case_margin = 0;  // 1: bf16 margin from the data-independent worst case (A/B only)
   int tighten_adaptive = 1;  // refresher pause grows with the elapsed kernel time (see UmmaArgs)
@@ -369,8 +381,21 @@ int launch_grid_rows(const Shard& S, int64_t rows) {
 
 // Append rows already resident at x32[S.n .. S.n+n): build shadow + norm bound.
 int ingest_rows(b2f_index* idx, Shard& S, int64_t n) {
+  if (!S.mu_set) {
+    // First rows of an empty shard: fix the centre.  Any vector is a valid centre (correctness never depends
+    // on it); the mean of the first rows is what shrinks ||p - mu|| — and with it the prefilter margin — for
+    // embeddings that share a large common component (LayerNorm outputs; reference model/models.py:136-145).
+    if (idx->center && idx->shadow && S.n == 0) {
+      const int64_t m = std::min<int64_t>(n, kMuRows);
+      const int blocks = static_cast<int>(std::min<int64_t>(m, kMuBlocks));
+      col_sum_partial_kernel<<<blocks, kRowF4, 0, S.stream>>>(S.x32, 0, m, S.mu_part);
+      col_mean_final_kernel<<<(kD + 255) / 256, 256, 0, S.stream>>>(S.mu_part, blocks, m, S.mu);
+      CU_TRY(cudaGetLastError());
+    }
+    S.mu_set = true;
+  }
   convert_rows_kernel<<<launch_grid_rows(S, n), 256, 0, S.stream>>>(S.x32, idx->shadow ? S.x16 : nullptr, S.n, n,
-                                                                    S.maxnorm2);
+                                                                    S.maxnorm2, S.mu);
   CU_TRY(cudaGetLastError());
   return B2F_OK;
 }
@@ -416,7 +441,7 @@ int ensure_pass_ws(Shard& S, int qp, int C) {
   dev_free(W.ovf); dev_free(W.margin); dev_free(W.gath); dev_free(W.cnt2);
   dev_free(W.hist); dev_free(W.hkey0); dev_free(W.hshift);
   B2F_TRY(dev_alloc(&W.gath, static_cast<size_t>(qp) * C));
-  B2F_TRY(dev_alloc(&W.cnt2, static_cast<size_t>(qp) * 128));
+  B2F_TRY(dev_alloc(&W.cnt2, static_cast<size_t>(qp) * 256));   // per (query, area): <= 128 pairs / 256 CTAs
   B2F_TRY(dev_alloc(&W.hist, static_cast<size_t>(qp) * kHistStride));
   B2F_TRY(dev_alloc(&W.hkey0, static_cast<size_t>(qp)));
   B2F_TRY(dev_alloc(&W.hshift, static_cast<size_t>(qp)));
@@ -454,8 +479,9 @@ int ensure_pin(Shard& S, size_t bytes) {
 //   mode 1 (fp32 scan):    eps = u_scan * ||q|| * P,  P = max ||p||   (Cauchy-Schwarz on sum |q_t p_t|).
 //   mode 2 (bf16 tensor):  s~ = fl(sum q^_t p^_t) with q^ = bf16(q), p^ = bf16(p).  Then
 //       |s~ - s| <= |sum q^ (p^ - p)| + |sum (q^ - q) p| + accumulation
-//                <= (1 + 2^-9) ||q|| E + e_q P + g ||q|| P,
-//     E = max ||p - p^|| (kept per shard at add time), e_q = ||q - q^||, g = 1.1e-4 >= 768 * 2^-23
+//                <= (1 + 2^-8) ||q|| E + e_q P + g ||q|| P,
+//     where p stands for the centred row p - mu and p^ for its bf16 shadow,
+//     E = max ||p - p^|| and P = max ||p|| (kept per shard at add time), e_q = ||q - q^||, g = 1.1e-4 >= 768 * 2^-23
 //     (fp32 accumulation of 768 exact products inside the tensor core, truncation allowed).
 // Every factor is an upper bound and every operation rounds up; `scale` (margin_ppm) multiplies the result.
 __global__ void pass_init_kernel(const float* __restrict__ qnorm, const float* __restrict__ qerr,
@@ -470,23 +496,29 @@ __global__ void pass_init_kernel(const float* __restrict__ qnorm, const float* _
     // the eight binades below R = (1 + 2^-6) * ||q|| * max||p|| >= |any prefilter score of q|; tau = -inf.
     for (int b = threadIdx.x; b < kHistStride; b += blockDim.x) hist[static_cast<int64_t>(q) * kHistStride + b] = 0u;
     if (threadIdx.x == 0) {
-      const float R = __fmul_ru(__fmul_ru(qnorm[q], __fsqrt_ru(__uint_as_float(maxnorm2_bits[0]))), 1.015625f);
+      const float R = __fmul_ru(__fmul_ru(qnorm[q], __fsqrt_ru(__uint_as_float(maxnorm2_bits[2]))), 1.015625f);
       const uint32_t top = fkey(R) >> 17;
       hkey0[q] = (top >= static_cast<uint32_t>(kHistBuckets - 1) ? top - (kHistBuckets - 1) : 0u) << 17;
       hshift[q] = 17;
-      tau[q] = -INFINITY;
     }
   }
   if (threadIdx.x == 0) {
-    const float P = __fsqrt_ru(__uint_as_float(maxnorm2_bits[0]));
+    // Every pass starts without a threshold: finalize_kernel filters on tau[q] whenever tightening is on,
+    // and a pass that ends inside the dense phase (shard smaller than the bootstrap) never writes it.
+    tau[q] = -INFINITY;
+    // tensor engine: scores are taken against the CENTRED rows p - mu (constant shift q.mu per query), so its
+    // bounds use Pc = max ||p - mu||; the fp32 scan reads the rows themselves: P = max ||p||
+    const float P = __fsqrt_ru(__uint_as_float(maxnorm2_bits[mode == 1 ? 0 : 2]));
     float eps = 0.f;
     if (mode == 1) {
       eps = __fmul_ru(__fmul_ru(qnorm[q], P), u_scan);
-    } else if (mode == 3) {   // worst-case bf16 bound 2^-8 * 1.002 + 1e-4 (A/B reference for mode 2)
-      eps = __fmul_ru(__fmul_ru(qnorm[q], P), 0.004014063f);
+    } else if (mode == 3) {   // data-independent worst case (A/B reference for mode 2): bf16 round-to-nearest has
+      // unit roundoff 2^-8, so E <= 2^-8 P, ||q^|| <= (1 + 2^-8) ||q||, e_q <= 2^-8 ||q||:
+      // 2^-8 (1 + 2^-8) + 2^-8 + 1.1e-4 < 0.007954
+      eps = __fmul_ru(__fmul_ru(qnorm[q], P), 0.007954f);
     } else if (mode == 2) {
       const float E = __fsqrt_ru(__uint_as_float(maxnorm2_bits[1]));
-      const float a = __fmul_ru(__fmul_ru(qnorm[q], E), 1.001953125f);
+      const float a = __fmul_ru(__fmul_ru(qnorm[q], E), 1.00390625f);   // ||bf16(q)|| <= (1 + 2^-8) ||q||
       const float b = __fmul_ru(qerr[q], P);
       const float c = __fmul_ru(__fmul_ru(qnorm[q], P), 1.1e-4f);
       eps = __fadd_ru(__fadd_ru(a, b), c);
@@ -545,9 +577,10 @@ struct PassPlan {
   int qp;       // max queries per pass
   int C;        // candidate capacity per query
   int64_t n0;   // rows of the dense (bootstrap) phase
-  int S;        // TS tensor engine: survivor area [0, S) of a list
-  int cap_p;    // TS tensor engine: private slots per (query, CTA pair) and launch
-  int variant;  // tensor engine variant: 1 = SS (queries in smem), 2 = TS (queries in TMEM)
+  int S;        // tensor engine: survivor area [0, S) of a list
+  int cap_p;    // TS variant: private slots per (query, CTA pair) and launch
+  int cap_a;    // QS variant: private slots per (query, CTA)
+  int variant;  // tensor engine variant: 0 = per pass (QS up to qs_max_q queries, TS above), 2 = TS, 3 = QS
 };
 
 PassPlan make_plan(const b2f_index* idx, const Shard& S, int path, int k, int64_t nq) {
@@ -556,40 +589,45 @@ PassPlan make_plan(const b2f_index* idx, const Shard& S, int path, int k, int64_
   p.exact = (path == B2F_PATH_SCAN_EXACT);
   p.S = 0;
   p.cap_p = 0;
+  p.cap_a = 0;
   p.variant = 0;
+  (void)nq;
   if (path == B2F_PATH_UMMA_BF16) {
-    // SS: MMA N follows the query count (no padding) but one pass holds <= 192 queries;
-    // TS: 256 queries per pass, MMA M always 256.  AUTO: whichever needs fewer tensor cycles.
-    p.variant = idx->umma_variant;
-    // AUTO = TS.  Measured on B200 (profiles/r01): in isolation TS streams 5.6-5.95 TB/s
-    // vs 5.4 TB/s for SS; under the sustained power cap both settle near 5.0 TB/s (TS becomes
-    // tensor-bound because M is always 256, SS stays short of in-flight bytes).  TS also takes 256
-    // queries per pass and needs no atomics.
-    if (p.variant == 0) p.variant = 2;
-    (void)nq;
-  }
-  if (path == B2F_PATH_UMMA_BF16 && p.variant == 1) {
-    p.qp = kSsMaxQ;
-    p.n0 = static_cast<int64_t>(S.max_pairs) * kSsTileRows;   // one wave of pair tiles
-    p.C = static_cast<int>(round_up(std::max<int64_t>(p.n0, 32ll * k), 256));
-  } else if (path == B2F_PATH_UMMA_BF16) {
+    // Two kernels share one list layout (survivors [0,S) + private areas).  TS: queries in TMEM, MMA M is
+    // always 256 query lanes, 256 queries per pass, areas per CTA pair.  QS: queries on the MMA N side
+    // (N = nq rounded up to 16), streamed from L2 next to the passages, areas per CTA.  AUTO decides per
+    // pass: QS while the batch leaves lanes unused in TS (profiles/r02: 173 queries -> N = 176, 31 % fewer
+    // tensor cycles), TS for (nearly) full passes.
+    p.variant = idx->umma_variant == 1 ? 3 : idx->umma_variant;
     p.qp = kUmmaMaxQ;
-    // bootstrap (dense) phase: whole tiles per CTA pair, at least 8k rows (and 4096) in total
+    // bootstrap (dense) phase of the phased TS schedules: whole tiles per CTA pair, at least 8k rows
     const int64_t wave = static_cast<int64_t>(S.max_pairs) * kTileRows;
     const int64_t t0 = (std::max<int64_t>(4096, 8ll * k) + wave - 1) / wave;
     p.n0 = t0 * wave;
-    p.S = static_cast<int>(round_up(std::max(1024, 4 * k), 256));
-    // expected appends per (query, pair) in a phase: 2 (margin) * (growth-1) * k / pairs; x2 safety
+    // survivors within the margin of the k-th score: ~k * (e^(z * 2eps / sigma) - 1) with z ~ 5 the tail slope
+    // at rank 100 of 4e7: ~200 for isotropic unit rows, ~700 for LayerNorm-like rows with a common mean after
+    // centring — 4096 leaves a factor of 5
+    p.S = static_cast<int>(round_up(std::max(4096, 4 * k), 256));
+    // expected appends per (query, area) in a phase: 2 (margin) * (growth-1) * k / areas; x2 safety
     // (with in-kernel tightening the pass rate follows k/rows_seen, far fewer appends; keep the bound)
     const int64_t expect = 4ll * (std::max(2, idx->growth) - 1) * k / S.max_pairs;
     p.cap_p = static_cast<int>(round_up(std::max<int64_t>(std::max<int64_t>(512, t0 * kTileRows), expect), 32));
-    p.C = p.S + S.max_pairs * p.cap_p;
+    p.cap_a = static_cast<int>(round_up(std::max<int64_t>(512, kQsTileRowsCta + expect / 2), 32));
+    p.C = p.S + std::max(S.max_pairs * p.cap_p, 2 * S.max_pairs * p.cap_a);
   } else {
     p.qp = kScanMaxQ;
     p.n0 = 16384;
-    p.C = static_cast<int>(round_up(std::max<int64_t>(p.n0, 32ll * k), 256));
+    // a phase of `growth` times the rows seen so far passes ~growth * k rows (plus the margin's share)
+    p.C = static_cast<int>(round_up(std::max<int64_t>(p.n0, (std::max(2, idx->growth) + 4ll) * k * 5 / 4), 256));
   }
   return p;
+}
+
+// Which tensor kernel runs a pass of nqp queries.
+int pass_variant(const b2f_index* idx, const PassPlan& plan, int nqp) {
+  if (plan.variant == 2 || plan.variant == 3) return plan.variant;
+  if (!idx->tighten || idx->bootstrap) return 2;      // the phased schedules exist for TS only
+  return nqp <= idx->qs_max_q ? 3 : 2;
 }
 
 // Enqueue one pass (<= plan.qp queries) on the shard stream.  q32p: the pass's fp32 queries
@@ -603,37 +641,69 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   const int64_t N = S.n;
   const int C = W.C;
   cudaStream_t s = S.stream;
-  const bool tensor = plan.path == B2F_PATH_UMMA_BF16 && plan.variant == 2;   // TS: segmented lists
-  const bool tensor_ss = plan.path == B2F_PATH_UMMA_BF16 && plan.variant == 1;
-  const bool one_launch = tensor && idx->tighten && !idx->bootstrap;   // no bootstrap: ONE scoring launch per pass
-  if (tensor) {
-    if (!W.areas_clean) {   // only after (re)allocation or after another engine used the lists
+  const int variant = plan.path == B2F_PATH_UMMA_BF16 ? pass_variant(idx, plan, nqp) : 0;
+  const bool tensor = variant == 2;      // TS: queries in TMEM, areas per CTA pair
+  const bool tensor_qs = variant == 3;   // QS: queries streamed on the N side, areas per CTA
+  const bool one_launch = tensor_qs || (tensor && idx->tighten && !idx->bootstrap);   // ONE scoring launch per pass
+  if (tensor && !one_launch) {
+    if (!W.areas_clean) {   // phased TS schedules gather whole areas: they must be all-zero between launches
       CU_TRY(cudaMemsetAsync(W.cand[0], 0, sizeof(uint64_t) * static_cast<size_t>(W.qp_cap) * W.C, s));
       CU_TRY(cudaMemsetAsync(W.cand[1], 0, sizeof(uint64_t) * static_cast<size_t>(W.qp_cap) * W.C, s));
       W.areas_clean = true;
     }
   } else {
-    W.areas_clean = false;  // flat lists overwrite the private areas
+    W.areas_clean = false;  // flat lists / one-launch passes leave records behind in the areas
   }
+  const int n_areas = tensor_qs ? 2 * S.max_pairs : S.max_pairs;
   const int margin_mode = plan.exact ? 0 : (plan.path == B2F_PATH_UMMA_BF16 ? (idx->worst_case_margin ? 3 : 2) : 1);
   pass_init_kernel<<<nqp, 128, 0, s>>>(qnormp, qerrp, S.maxnorm2, margin_mode,
                                        static_cast<float>(idx->margin_ppm * 1e-6 * 1.0000001), static_cast<float>(kUScan),
-                                       W.margin, W.cnt, W.ovf, tensor ? W.cnt2 : nullptr, S.max_pairs,
+                                       W.margin, W.cnt, W.ovf, (tensor || tensor_qs) ? W.cnt2 : nullptr, n_areas,
                                        one_launch ? W.hist : nullptr, W.hkey0, W.hshift, W.tau);
   st.launches += 1;
 
-  int cur = 0;
-  CUtensorMap tmap_p, tmap_pf, tmap_q;
-  int ss_cols = 0, ss_stages = 0, ss_smem = 0;
-  if (tensor_ss) {
-    ss_cols = static_cast<int>(round_up(nqp, 16));
-    ss_stages = umma_ss_stages(ss_cols);
-    ss_smem = umma_ss_smem_bytes(ss_cols, ss_stages);
+  if (tensor_qs) {
+    // ---- QS: one launch over the whole shard, then the fused last step ----
+    const int n_cols = static_cast<int>(round_up(nqp, 16));
+    const QsPlan qp = umma_qs_plan(n_cols, idx->umma_variant == 1 ? kNumKBlocks : idx->qs_resident_kb, idx->qs_q_stages);
+    CUtensorMap tmap_p, tmap_q;
     const uint64_t srows = static_cast<uint64_t>(shadow_rows_padded(N)) * kNumKBlocks;
     B2F_TRY(make_tmap_bf16(&tmap_p, S.x16, srows, kBlockK, kShadowTileRows));        // one K-block of a 32-row tile
-    B2F_TRY(make_tmap_bf16(&tmap_pf, S.x16, srows, kBlockK, 4 * kShadowTileRows));   // 16 KB prefetch chunks
-    B2F_TRY(make_tmap_bf16(&tmap_q, q16p, static_cast<uint64_t>(ss_cols), kD, static_cast<uint32_t>(ss_cols / 2)));
+    B2F_TRY(make_tmap_bf16(&tmap_q, q16p, static_cast<uint64_t>(n_cols), kD, static_cast<uint32_t>(n_cols / 2)));
+    const int te = static_cast<int>((N + kQsTileRows - 1) / kQsTileRows);
+    UmmaQsArgs a;
+    a.n_rows = N; a.tile_begin = 0; a.tile_end = te; a.n_cols = n_cols; a.nq = nqp;
+    a.a_stages = qp.a_stages; a.q_stages = qp.q_stages; a.resident_kb = qp.resident_kb; a.q16 = q16p;
+    a.cand = W.cand[0]; a.C = C; a.S = plan.S; a.cap_p = plan.cap_a; a.n_areas = n_areas; a.cnt2 = W.cnt2;
+    a.tau = W.tau; a.ovf = W.ovf; a.err = W.err; a.tighten = idx->tighten; a.tighten_adaptive = idx->tighten_adaptive;
+    a.k = k; a.margin = W.margin; a.hist = W.hist; a.hkey0 = W.hkey0; a.hshift = W.hshift;
+    const int pairs = std::min(S.max_pairs, te);
+    {
+      ProfScope ps(idx, S, 0);
+      umma_qs_score_select_kernel<<<2 * pairs, kUmmaThreads, qp.smem_bytes, s>>>(tmap_p, tmap_q, a);
+    }
+    CU_TRY(cudaGetLastError());
+    st.score_rows += static_cast<double>(N);
+    st.launches += 1;
+    st.phases += 1;
+    st.qs_passes += 1;
+    ProfScope ps(idx, S, 1);
+    int PS = 1024;
+    while (PS < plan.S) PS <<= 1;
+    int P = 8192;
+    while (P < PS) P <<= 1;
+    finalize_kernel<<<nqp, kFinThreads, static_cast<size_t>(P + PS) * sizeof(uint64_t), s>>>(
+        W.cand[0], W.gath, W.cnt, C, k, W.margin, plan.S, plan.cap_a, n_areas, W.cnt2, W.ovf, ovf_dst, q32p,
+        S.x32, S.segs_d, static_cast<int>(S.segs.size()), S.has_ids ? S.idmap : nullptr, D_out, I_out, out_stride, P,
+        W.tau);
+    CU_TRY(cudaGetLastError());
+    st.launches += 1;
+    st.passes += 1;
+    return B2F_OK;
   }
+
+  int cur = 0;
+  CUtensorMap tmap_p;
   if (tensor) {
     // shadow = [row tiles x 12 K-blocks x tile rows, 64 columns] bf16; box = 128 x 128 B = 16 KB
     B2F_TRY(make_tmap_bf16(&tmap_p, S.x16, static_cast<uint64_t>(shadow_rows_padded(N)) * kNumKBlocks, kBlockK,
@@ -653,22 +723,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     else if (tensor && idx->tighten) end = N;   // thresholds are tightened inside the kernel
     else end = std::min<int64_t>(N, begin * std::max(2, idx->growth));
     int n_override = -1;
-    if (tensor_ss) {
-      const int tb = static_cast<int>(begin / kSsTileRows);
-      const int te = static_cast<int>((end + kSsTileRows - 1) / kSsTileRows);
-      if (end < N) end = static_cast<int64_t>(te) * kSsTileRows;  // phases end on tile boundaries
-      UmmaSsArgs a;
-      a.n_rows = N; a.tile_begin = tb; a.tile_end = te; a.n_cols = ss_cols; a.nq = nqp; a.stages = ss_stages;
-      a.prefetch = idx->l2_prefetch; a.dense = dense ? 1 : 0; a.dense_row0 = 0; a.cand = W.cand[cur]; a.cnt = W.cnt;
-      a.C = C; a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
-      const int pairs = std::min(S.max_pairs, te - tb);
-      {
-        ProfScope ps(idx, S, 0);
-        umma_ss_score_select_kernel<<<2 * pairs, kUmmaThreads, ss_smem, s>>>(tmap_p, tmap_pf, tmap_q, a);
-      }
-      st.score_rows += static_cast<double>(std::min<int64_t>(N, static_cast<int64_t>(te) * kSsTileRows) - begin);
-      if (dense) n_override = (te - tb) * kSsTileRows;
-    } else if (tensor) {
+    if (tensor) {
       const int tb = static_cast<int>(begin / kTileRows);
       const int te = static_cast<int>((end + kTileRows - 1) / kTileRows);
       if (end < N) end = static_cast<int64_t>(te) * kTileRows;  // phases end on tile boundaries
@@ -799,7 +854,7 @@ int enqueue_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k
     static bool attr_set[64] = {false};
     if (!attr_set[S.dev & 63]) {
       CU_TRY(cudaFuncSetAttribute(umma_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmemBytes));
-      CU_TRY(cudaFuncSetAttribute(umma_ss_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemLimit));
+      CU_TRY(cudaFuncSetAttribute(umma_qs_score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQsSmemLimit));
       CU_TRY(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 8));   // P + PS records
       CU_TRY(cudaFuncSetAttribute(bootstrap_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
       attr_set[S.dev & 63] = true;
@@ -965,8 +1020,11 @@ int b2f_create(int d, const int* devices, int n_dev, b2f_index** out) {
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&S.maxnorm2), 2 * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(S.maxnorm2, 0, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&S.maxnorm2), 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(S.maxnorm2, 0, 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&S.mu), kD * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(S.mu, 0, kD * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&S.mu_part), static_cast<size_t>(kMuBlocks) * kD * sizeof(float));
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       std::string m = std::string("device setup failed: ") + cudaGetErrorString(e);
@@ -1018,6 +1076,7 @@ void b2f_destroy(b2f_index* idx) {
     if (S.stream) cudaStreamSynchronize(S.stream);
     Workspace& W = S.ws;
     dev_free(S.x32); dev_free(S.x16); dev_free(S.idmap); dev_free(S.maxnorm2); dev_free(S.segs_d);
+    dev_free(S.mu); dev_free(S.mu_part);
     dev_free(W.cand[0]); dev_free(W.cand[1]); dev_free(W.cnt); dev_free(W.tau); dev_free(W.tauP);
     dev_free(W.ovf); dev_free(W.margin); dev_free(W.err); dev_free(W.q32); dev_free(W.q16);
     dev_free(W.gath); dev_free(W.cnt2); dev_free(W.hist); dev_free(W.hkey0); dev_free(W.hshift);
@@ -1138,9 +1197,11 @@ int b2f_add_synthetic(b2f_index* idx, int shard, int64_t first_row, int64_t n, u
   B2F_TRY(ensure_capacity(idx, S, S.n + n));
   const uint32_t k0 = static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(stream);
   const uint32_t k1 = static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(stream >> 32) ^ 0x5eedu;
-  synth_rows_kernel<<<launch_grid_rows(S, n), 256, 0, S.stream>>>(S.x32, idx->shadow ? S.x16 : nullptr, S.n,
-                                                                  first_row, n, k0, k1, norm, S.maxnorm2);
+  synth_rows_kernel<<<launch_grid_rows(S, n), 256, 0, S.stream>>>(S.x32, S.n, first_row, n, k0, k1, norm,
+                                                                  idx->synth_mean_shift, static_cast<uint32_t>(seed),
+                                                                  static_cast<uint32_t>(seed >> 32) ^ 0x5eedu);
   CU_TRY(cudaGetLastError());
+  B2F_TRY(ingest_rows(idx, S, n));
   push_seg(S, S.n, n, id_base);
   S.n += n;
   idx->ntotal += n;
@@ -1169,7 +1230,9 @@ int b2f_reset(b2f_index* idx) {
     S.n = 0;
     S.segs.clear();
     S.has_ids = false;
-    CU_TRY(cudaMemsetAsync(S.maxnorm2, 0, 2 * sizeof(unsigned int), S.stream));
+    CU_TRY(cudaMemsetAsync(S.maxnorm2, 0, 4 * sizeof(unsigned int), S.stream));
+    CU_TRY(cudaMemsetAsync(S.mu, 0, kD * sizeof(float), S.stream));
+    S.mu_set = false;
     if (!idx->keep_on_reset) {
       dev_free(S.x32); dev_free(S.x16); dev_free(S.idmap);
       S.cap = 0;
@@ -1478,8 +1541,23 @@ int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
   } else if (k == "keep_on_reset") {
     idx->keep_on_reset = value ? 1 : 0;
   } else if (k == "umma_variant") {
-    if (value < 0 || value > 2) return fail(B2F_ERR_INVALID, "umma_variant must be 0 (auto), 1 (SS) or 2 (TS)");
+    if (value < 0 || value > 3) return fail(B2F_ERR_INVALID, "umma_variant must be 0 (auto), 1 (QS, resident queries), 2 (TS) or 3 (QS)");
     idx->umma_variant = static_cast<int>(value);
+  } else if (k == "qs_max_q") {
+    if (value < 0 || value > kQsMaxCols) return fail(B2F_ERR_INVALID, "qs_max_q must be in [0, 256]");
+    idx->qs_max_q = static_cast<int>(value);
+  } else if (k == "qs_resident_kb") {
+    if (value < 0 || value > kNumKBlocks) return fail(B2F_ERR_INVALID, "qs_resident_kb must be in [0, 12]");
+    idx->qs_resident_kb = static_cast<int>(value);
+  } else if (k == "qs_q_stages") {
+    if (value < 2 || value > kQsMaxQStages) return fail(B2F_ERR_INVALID, "qs_q_stages must be in [2, 4]");
+    idx->qs_q_stages = static_cast<int>(value);
+  } else if (k == "center") {
+    if (idx->ntotal > 0) return fail(B2F_ERR_INVALID, "center can only be changed on an empty index");
+    idx->center = value ? 1 : 0;
+  } else if (k == "synth_mean_shift") {
+    if (value < 0 || value > 4096) return fail(B2F_ERR_INVALID, "synth_mean_shift must be in [0, 4096]");
+    idx->synth_mean_shift = static_cast<int>(value);
   } else if (k == "l2_prefetch") {
     if (value < 0 || value > 8) return fail(B2F_ERR_INVALID, "l2_prefetch must be 0 (off) or a distance of 1..8 tiles");
     idx->l2_prefetch = static_cast<int>(value);
@@ -1511,13 +1589,14 @@ int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
   Stats s = idx->stats;          // index-level counters (merges, exchange) + the sum over shards
   for (const Shard& S : idx->shards) {
     s.launches += S.stats.launches; s.phases += S.stats.phases; s.candidates += S.stats.candidates;
-    s.fallback_queries += S.stats.fallback_queries; s.passes += S.stats.passes; s.score_ms += S.stats.score_ms;
+    s.fallback_queries += S.stats.fallback_queries; s.passes += S.stats.passes; s.qs_passes += S.stats.qs_passes; s.score_ms += S.stats.score_ms;
     s.score_launches += S.stats.score_launches; s.score_rows += S.stats.score_rows; s.select_ms += S.stats.select_ms;
     s.xchg_ms += S.stats.xchg_ms;
   }
   if (!idx->shards.empty()) {
     s.path = idx->shards[0].stats.path;
     s.passes = idx->shards[0].stats.passes;   // passes / phases are per search, not per shard
+    s.qs_passes = idx->shards[0].stats.qs_passes;
     s.phases = idx->shards[0].stats.phases;
   }
   if (k == "launches") *out = s.launches;
@@ -1526,6 +1605,7 @@ int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
   else if (k == "fallback_queries") *out = s.fallback_queries;
   else if (k == "path") *out = s.path;
   else if (k == "passes") *out = s.passes;
+  else if (k == "qs_passes") *out = s.qs_passes;
   else if (k == "score_ms") *out = s.score_ms;
   else if (k == "score_launches") *out = s.score_launches;
   else if (k == "score_rows") *out = s.score_rows;

@@ -404,7 +404,28 @@ __device__ __forceinline__ FinFront fin_front(const uint64_t* __restrict__ list,
     if (lane == 0 && c) atomicAdd(&sm.nvalid, static_cast<unsigned int>(c));
     __syncthreads();
   }
-  const int upper = m + static_cast<int>(sm.nvalid);
+  int upper = m + static_cast<int>(sm.nvalid);
+  if (upper > P && Tlow != 0ull) {
+    // The raw list does not fit the shared-memory buffer, but most of it predates the thresholds (the
+    // first tile of every CTA passes unfiltered: 148 x 128 records per query in the QS variant) and falls
+    // to the Tlow filter below: count what survives it before sending the list through global memory.
+    __syncthreads();
+    int c = 0;
+    for (int i = tid; i < m; i += kFinThreads) c += (list[i] != 0ull && list[i] >= Tlow);
+    for (int p = warp; p < max_pairs; p += kFinThreads / 32) {
+      const int cp = min(cnt2q[p], cap_p);
+      const uint64_t* src = list + S + static_cast<int64_t>(p) * cap_p;
+      for (int e = lane; e < cp; e += 32) c += (src[e] >= Tlow);
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+    if (lane == 0 && c) atomicAdd(&sm.count, static_cast<unsigned int>(c));
+    __syncthreads();
+    upper = static_cast<int>(sm.count);
+    __syncthreads();
+    if (tid == 0) sm.count = 0;
+    __syncthreads();
+  }
   uint64_t* in = (upper <= P) ? bufA : gath_q;
 
   // ---- 2. gather + filter: keep the non-empty records >= Tlow.  Tlow is any lower bound of the final

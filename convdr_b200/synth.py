@@ -10,6 +10,11 @@ Row r of stream (seed, stream):
     x[t] = fl32(component[t]) * inv
 with k0 = lo32(seed) ^ lo32(stream), k1 = hi32(seed) ^ hi32(stream) ^ 0x5eed.
 Streams used by the benchmark: passages stream 0, queries stream 1 (seed 0).
+
+`mean_shift = M > 0` adds sign[t] * M to component[t] before the normalisation, sign[t] = +-1 from the low
+bit of word t of Philox(counter=(0xffffffff, 0xffffffff, c, 0x6d65616e), key=(lo32(seed), hi32(seed) ^ 0x5eed)):
+one fixed direction per seed, shared by passages and queries.  The rows then look like LayerNorm outputs
+with a common mean (reference model/models.py:136-145): cos(p, p') ~ M^2 / (M^2 + 147.8^2); M = 443 -> 0.9.
 """
 from __future__ import annotations
 
@@ -50,10 +55,21 @@ def _bytesum(w):
             + (w >> np.uint64(24))).astype(np.int64) - 510
 
 
-def rows(row_ids, seed: int = 0, stream: int = 0, norm: float = 1.0) -> np.ndarray:
+def mean_signs(seed: int = 0) -> np.ndarray:
+    """int64 [768] of +-1: the fixed direction of the common mean for this seed."""
+    chunk = np.arange(DIM // 4, dtype=np.uint64)
+    ones = np.full_like(chunk, 0xFFFFFFFF)
+    w = philox4x32_10(ones, ones, chunk, np.full_like(chunk, 0x6D65616E), int(seed) & 0xFFFFFFFF,
+                      ((int(seed) >> 32) & 0xFFFFFFFF) ^ 0x5EED)
+    bits = np.stack([x & np.uint64(1) for x in w], axis=-1).reshape(DIM).astype(np.int64)
+    return 2 * bits - 1
+
+
+def rows(row_ids, seed: int = 0, stream: int = 0, norm: float = 1.0, mean_shift: int = 0) -> np.ndarray:
     """float32 [len(row_ids), 768]: the given rows of stream (seed, stream)."""
     row_ids = np.asarray(row_ids, dtype=np.uint64).reshape(-1)
     k0, k1 = _keys(int(seed), int(stream))
+    shift = mean_signs(seed) * int(mean_shift) if mean_shift else None
     out = np.empty((row_ids.size, DIM), dtype=np.float32)
     chunk = np.arange(DIM // 4, dtype=np.uint64)[None, :]
     step = 8192
@@ -65,6 +81,8 @@ def rows(row_ids, seed: int = 0, stream: int = 0, norm: float = 1.0) -> np.ndarr
         c3 = np.zeros_like(c2)
         w = philox4x32_10(c0, c1, c2, c3, k0, k1)
         comp = np.stack([_bytesum(x) for x in w], axis=-1).reshape(r.shape[0], DIM)  # [rows, 192, 4] -> 768
+        if shift is not None:
+            comp = comp + shift[None, :]
         ss = (comp * comp).sum(axis=1)
         with np.errstate(divide="ignore"):
             inv = np.float32(norm) / np.sqrt(ss.astype(np.float32))
@@ -73,6 +91,6 @@ def rows(row_ids, seed: int = 0, stream: int = 0, norm: float = 1.0) -> np.ndarr
     return out
 
 
-def block(first_row: int, n: int, seed: int = 0, stream: int = 0, norm: float = 1.0) -> np.ndarray:
+def block(first_row: int, n: int, seed: int = 0, stream: int = 0, norm: float = 1.0, mean_shift: int = 0) -> np.ndarray:
     """float32 [n, 768]: rows first_row .. first_row+n-1."""
-    return rows(np.arange(first_row, first_row + n, dtype=np.uint64), seed, stream, norm)
+    return rows(np.arange(first_row, first_row + n, dtype=np.uint64), seed, stream, norm, mean_shift)

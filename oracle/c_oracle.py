@@ -23,6 +23,11 @@ def load():
                                            C.c_void_p, C.c_void_p]
         lib.oracle_synth_rows.restype = None
         lib.oracle_synth_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_float]
+        lib.oracle_synth_rows2.restype = None
+        lib.oracle_synth_rows2.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_float, C.c_int]
+        lib.oracle_topk_synth_f64.restype = None
+        lib.oracle_topk_synth_f64.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_uint64,
+                                              C.c_uint64, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -37,7 +42,20 @@ def knn_ip_heap(x: np.ndarray, xb: np.ndarray, k: int):
     return D, I
 
 
-def synth_block(first_row: int, n: int, seed: int = 0, stream: int = 0, norm: float = 1.0) -> np.ndarray:
+def synth_block(first_row: int, n: int, seed: int = 0, stream: int = 0, norm: float = 1.0,
+                mean_shift: int = 0) -> np.ndarray:
     out = np.empty((n, 768), dtype=np.float32)
-    load().oracle_synth_rows(out.ctypes.data, first_row, n, seed, stream, norm)
+    load().oracle_synth_rows2(out.ctypes.data, first_row, n, seed, stream, norm, mean_shift)
     return out
+
+
+def topk_synth_f64(Q: np.ndarray, k: int, first_row: int, n_rows: int, seed: int = 0, stream: int = 0,
+                   norm: float = 1.0, mean_shift: int = 0):
+    """float64 ground truth (D [nq,k], I [nq,k] global rows, order (score desc, row asc)) over rows
+    [first_row, first_row + n_rows) of a synthetic stream, regenerated block by block on all host threads."""
+    Q = np.ascontiguousarray(Q, dtype=np.float32)
+    D = np.empty((Q.shape[0], k), dtype=np.float64)
+    I = np.empty((Q.shape[0], k), dtype=np.int64)
+    load().oracle_topk_synth_f64(Q.ctypes.data, Q.shape[0], k, first_row, n_rows, seed, stream, norm, mean_shift,
+                                 D.ctypes.data, I.ctypes.data)
+    return D, I

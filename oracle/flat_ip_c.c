@@ -86,9 +86,17 @@ static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
   }
 }
 
-void oracle_synth_rows(float* out, int64_t first_row, int64_t n, uint64_t seed, uint64_t stream, float norm) {
+void oracle_synth_rows2(float* out, int64_t first_row, int64_t n, uint64_t seed, uint64_t stream, float norm,
+                        int mean_shift) {
   const uint32_t k0 = (uint32_t)seed ^ (uint32_t)stream;
   const uint32_t k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(stream >> 32) ^ 0x5eedu;
+  /* fixed sign vector of the common mean direction: one per seed, shared by every stream */
+  int shift[768];
+  for (uint32_t ch = 0; ch < 192; ++ch) {
+    uint32_t c[4] = {0xffffffffu, 0xffffffffu, ch, 0x6d65616eu};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x5eedu);
+    for (int j = 0; j < 4; ++j) shift[4 * ch + j] = mean_shift ? ((c[j] & 1u) ? mean_shift : -mean_shift) : 0;
+  }
 #pragma omp parallel for schedule(static)
   for (int64_t r = 0; r < n; ++r) {
     const uint64_t row = (uint64_t)(first_row + r);
@@ -99,7 +107,7 @@ void oracle_synth_rows(float* out, int64_t first_row, int64_t n, uint64_t seed, 
       philox4x32_10(c, k0, k1);
       for (int j = 0; j < 4; ++j) {
         const uint32_t w = c[j];
-        const int v = (int)((w & 0xffu) + ((w >> 8) & 0xffu) + ((w >> 16) & 0xffu) + (w >> 24)) - 510;
+        const int v = (int)((w & 0xffu) + ((w >> 8) & 0xffu) + ((w >> 16) & 0xffu) + (w >> 24)) - 510 + shift[4 * ch + j];
         comp[4 * ch + j] = v;
         ss += (int64_t)v * v;
       }
@@ -109,4 +117,114 @@ void oracle_synth_rows(float* out, int64_t first_row, int64_t n, uint64_t seed, 
     float* o = out + r * 768;
     for (int t = 0; t < 768; ++t) o[t] = (float)comp[t] * inv;
   }
+}
+
+void oracle_synth_rows(float* out, int64_t first_row, int64_t n, uint64_t seed, uint64_t stream, float norm) {
+  oracle_synth_rows2(out, first_row, n, seed, stream, norm, 0);
+}
+
+/* ---- fp64 ground truth over a synthetic collection that is never materialised ----
+ * For every query: the k best rows of stream (seed, stream), rows [first_row, first_row + n_rows), by the
+ * float64 inner product (products of the fp32 values exact in double, sequential sum), order (score desc,
+ * row asc); ids are the global row numbers.  Rows are regenerated in blocks by each OpenMP thread (the
+ * host twin of synth_rows_kernel above), scored against all queries at once (independent accumulators per
+ * query and per row of a 4-row group, so the loop pipelines) and offered to per-thread k-entry min-heaps,
+ * which are merged at the end.  This is what lets bench.py check the engine's answer at the full 38.6M-row
+ * size without 118 GB of host memory.  Restates `index.search` of the reference
+ * (drivers/run_convdr_inference.py:182) in exact arithmetic. */
+typedef struct { double s; int64_t id; } tk_ent;
+
+/* a precedes b in the result order */
+static inline int tk_better(double sa, int64_t ia, double sb, int64_t ib) { return sa > sb || (sa == sb && ia < ib); }
+
+static void tk_sift_down(tk_ent* h, int k, int i) {   /* min-heap: root = worst kept entry */
+  const tk_ent v = h[i];
+  for (;;) {
+    int c = 2 * i + 1;
+    if (c >= k) break;
+    if (c + 1 < k && tk_better(h[c].s, h[c].id, h[c + 1].s, h[c + 1].id)) c += 1;   /* pick the worse child */
+    if (!tk_better(v.s, v.id, h[c].s, h[c].id)) break;
+    h[i] = h[c];
+    i = c;
+  }
+  h[i] = v;
+}
+
+static void tk_offer(tk_ent* h, int k, double s, int64_t id) {
+  if (tk_better(s, id, h[0].s, h[0].id)) { h[0].s = s; h[0].id = id; tk_sift_down(h, k, 0); }
+}
+
+static int tk_cmp(const void* a, const void* b) {
+  const tk_ent* x = (const tk_ent*)a; const tk_ent* y = (const tk_ent*)b;
+  if (tk_better(x->s, x->id, y->s, y->id)) return -1;
+  if (tk_better(y->s, y->id, x->s, x->id)) return 1;
+  return 0;
+}
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+void oracle_topk_synth_f64(const float* Q, int64_t nq, int k, int64_t first_row, int64_t n_rows, uint64_t seed,
+                           uint64_t stream, float norm, int mean_shift, double* D, int64_t* I) {
+  int nthreads = 1;
+#ifdef _OPENMP
+  nthreads = omp_get_max_threads();
+#endif
+  /* queries transposed to double [768][nq]: the inner loop runs over queries (independent lanes) */
+  double* Qt = (double*)malloc(sizeof(double) * 768 * (size_t)nq);
+  for (int64_t q = 0; q < nq; ++q)
+    for (int t = 0; t < 768; ++t) Qt[(size_t)t * nq + q] = (double)Q[q * 768 + t];
+  tk_ent* heaps = (tk_ent*)malloc(sizeof(tk_ent) * (size_t)nthreads * nq * k);
+  for (size_t i = 0; i < (size_t)nthreads * nq * k; ++i) { heaps[i].s = -INFINITY; heaps[i].id = INT64_MAX; }
+  const int64_t BLK = 1024;
+  const int64_t nblk = (n_rows + BLK - 1) / BLK;
+#pragma omp parallel
+  {
+    int tid = 0;
+#ifdef _OPENMP
+    tid = omp_get_thread_num();
+#endif
+    tk_ent* my = heaps + (size_t)tid * nq * k;
+    float* rows = (float*)malloc(sizeof(float) * BLK * 768);
+    double* acc = (double*)malloc(sizeof(double) * 4 * (size_t)nq);
+#pragma omp for schedule(dynamic, 4)
+    for (int64_t b = 0; b < nblk; ++b) {
+      const int64_t r0 = b * BLK, m = (r0 + BLK <= n_rows) ? BLK : n_rows - r0;
+      /* serial generation inside the thread (the parallel-for inside oracle_synth_rows2 is nested: 1 thread) */
+      oracle_synth_rows2(rows, first_row + r0, m, seed, stream, norm, mean_shift);
+      for (int64_t r = 0; r < m; r += 4) {
+        const int g = (int)((m - r) < 4 ? (m - r) : 4);
+        for (int j = 0; j < 4 * nq; ++j) acc[j] = 0.0;
+        for (int t = 0; t < 768; ++t) {
+          const double* qt = Qt + (size_t)t * nq;
+          for (int u = 0; u < g; ++u) {
+            const double p = (double)rows[(r + u) * 768 + t];
+            double* a = acc + (size_t)u * nq;
+            for (int64_t q = 0; q < nq; ++q) a[q] += qt[q] * p;
+          }
+        }
+        for (int u = 0; u < g; ++u)
+          for (int64_t q = 0; q < nq; ++q) tk_offer(my + (size_t)q * k, k, acc[(size_t)u * nq + q], first_row + r0 + r + u);
+      }
+    }
+    free(rows);
+    free(acc);
+  }
+  /* merge the per-thread heaps */
+  tk_ent* all = (tk_ent*)malloc(sizeof(tk_ent) * (size_t)nthreads * k);
+  for (int64_t q = 0; q < nq; ++q) {
+    size_t n = 0;
+    for (int t = 0; t < nthreads; ++t)
+      for (int i = 0; i < k; ++i) {
+        const tk_ent e = heaps[((size_t)t * nq + q) * k + i];
+        if (e.id != INT64_MAX) all[n++] = e;
+      }
+    qsort(all, n, sizeof(tk_ent), tk_cmp);
+    for (int i = 0; i < k; ++i) {
+      D[q * k + i] = (size_t)i < n ? all[i].s : -INFINITY;
+      I[q * k + i] = (size_t)i < n ? all[i].id : -1;
+    }
+  }
+  free(all); free(heaps); free(Qt);
 }

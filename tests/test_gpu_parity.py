@@ -17,15 +17,18 @@ from oracle import c_oracle, flat_ip
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PATHS = ["scan_f32", "scan_exact", "umma_ss", "umma_ts"]   # umma_*: the two tensor-engine variants
+# umma_*: the tensor-engine variants — qs (queries streamed on the MMA N side, the default up to 208 queries per
+# pass), qsr (same kernel, every query K-block resident in shared memory), ts (queries in TMEM)
+PATHS = ["scan_f32", "scan_exact", "umma_qs", "umma_qsr", "umma_ts"]
+UMMA_VARIANT = {"umma_qsr": 1, "umma_ts": 2, "umma_qs": 3}
 RTOL = 1e-5          # the tolerance north_star states
 RTOL_TRUTH = 1e-6    # what the exact rescoring actually delivers vs float64
 
 
 def make_index(path, P=None, devices=None, **opts):
     idx = FlatIPIndex(768, devices=devices)
-    if path in ("umma_ss", "umma_ts"):
-        idx.set_option("umma_variant", 1 if path == "umma_ss" else 2)
+    if path in UMMA_VARIANT:
+        idx.set_option("umma_variant", UMMA_VARIANT[path])
         path = "umma_bf16"
     idx.set_option("path", path)
     for k, v in opts.items():
@@ -67,7 +70,9 @@ def test_config1_100k_173q_top100(path, c1_data):
     r = check_against_oracle(D, I, P, Q, 100)
     assert r["exact_rows"] >= 170
     assert idx.stat("fallback_queries") == 0
-    assert int(idx.stat("path")) == {"scan_f32": 1, "scan_exact": 2, "umma_ss": 3, "umma_ts": 3}[path]
+    assert int(idx.stat("path")) == {"scan_f32": 1, "scan_exact": 2}.get(path, 3)
+    if path in UMMA_VARIANT:
+        assert idx.stat("qs_passes") == (0 if path == "umma_ts" else 1)
     assert idx.stat("launches") > 0
 
 
@@ -82,7 +87,7 @@ def test_results_are_bitwise_path_independent(path, c1_data):
     np.testing.assert_array_equal(D, D0)
 
 
-@pytest.mark.parametrize("path", ["scan_f32", "umma_ss", "umma_ts"])
+@pytest.mark.parametrize("path", ["scan_f32", "umma_qs", "umma_qsr", "umma_ts"])
 def test_top1000_selection_pressure(path, c1_data):
     P, Q = c1_data  # BASELINE config 2's k = 1000 (gen_ranking_data.py negatives), reduced rows
     idx = make_index(path, P)
@@ -187,6 +192,56 @@ def test_non_unit_norm_rows_scale_28(path):
     Q = c_oracle.synth_block(0, 19, seed=4, stream=1, norm=28.0)
     D, I = make_index(path, P).search(Q, 50)
     check_against_oracle(D, I, P, Q, 50)
+
+
+@pytest.mark.parametrize("path", ["umma_qs", "umma_qsr", "umma_ts", "scan_f32"])
+@pytest.mark.parametrize("center", [1, 0])
+def test_rows_with_a_common_mean_like_layernorm_outputs(path, center):
+    """Embeddings that share a large mean component (cos(p, p') ~ 0.9, norm 28: what LayerNorm-ed ANCE
+    vectors look like, reference model/models.py:136-145).  Scores are ~706 +- 3.4, so a Cauchy-Schwarz
+    margin on the full norms (2 eps ~ 3.7) would put tens of thousands of rows inside the margin of the
+    100th score.  With the rows centred at add time the margin follows ||p - mu|| ~ 9 instead: no list
+    overflows and the result is the fp64 truth.  center=0 must stay correct (it may fall back)."""
+    P = c_oracle.synth_block(0, 100000, seed=51, norm=28.0, mean_shift=443)
+    Q = c_oracle.synth_block(0, 64, seed=51, stream=1, norm=28.0, mean_shift=443)
+    idx = make_index(path, None, center=center)
+    idx.add(P)
+    D, I = idx.search(Q, 100)
+    check_against_oracle(D, I, P, Q, 100, also_fp32_oracle=False)
+    if center:
+        assert idx.stat("fallback_queries") == 0
+
+
+def test_device_synthetic_rows_with_mean_shift_are_bit_identical_to_host():
+    idx = make_index("auto", None, synth_mean_shift=443)
+    idx.add_synthetic(3000, first_row=777, seed=5, stream=0, norm=28.0)
+    want = synth.block(777, 3000, seed=5, stream=0, norm=28.0, mean_shift=443)
+    np.testing.assert_array_equal(idx.reconstruct_n(0, 3000), want)
+    Q = c_oracle.synth_block(0, 9, seed=5, stream=1, norm=28.0, mean_shift=443)
+    D, I = idx.search(Q, 10)
+    Do, Io = flat_ip.truth_fp64(Q, want, 10)
+    np.testing.assert_array_equal(I, Io + 777)
+    assert idx.stat("fallback_queries") == 0
+
+
+def test_bootstrap_schedule_on_a_shard_smaller_than_the_bootstrap_ignores_stale_thresholds():
+    """with bootstrap=1 a pass over a shard that fits the dense phase never ran
+    bootstrap_select_kernel, and finalize_kernel filtered on thresholds left behind by the previous
+    search.  Every pass now starts from tau = -inf."""
+    P = c_oracle.synth_block(0, 3000, seed=61)
+    idx = make_index("umma_ts", P, bootstrap=1)
+    Qa = c_oracle.synth_block(0, 40, seed=61, stream=1, norm=50.0)     # leaves large thresholds behind
+    idx.search(Qa, 10)
+    big = make_index("umma_ts", c_oracle.synth_block(0, 60000, seed=62), bootstrap=1)
+    big.search(Qa, 10)
+    Qb = c_oracle.synth_block(0, 40, seed=63, stream=1, norm=0.01)     # every score far below them
+    for ix, PP in ((idx, P),):
+        D, I = ix.search(Qb, 10)
+        check_against_oracle(D, I, PP, Qb, 10)
+    big.reset()
+    big.add(P)
+    D, I = big.search(Qb, 10)
+    check_against_oracle(D, I, P, Qb, 10)
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -322,10 +377,16 @@ def test_in_kernel_threshold_tightening_gives_identical_results(c1_data):
 def test_auto_policy_and_invalid_arguments():
     P = c_oracle.synth_block(0, 20000, seed=13)
     idx = make_index("auto", P)
+    # AUTO: the tensor engine for every batch size (it streams half the bytes of the fp32 scan and wins from
+    # one query on — profiles/r01s2_sweep_8p8M_*.json); per pass, QS (MMA N = batch rounded to 16) up to 208
+    # queries, TS (256 query lanes) above
+    for nq, passes, qs in ((2, 1, 1), (64, 1, 1), (208, 1, 1), (209, 1, 0), (256, 1, 0), (300, 2, 1)):
+        idx.search(c_oracle.synth_block(0, nq, stream=1), 5)
+        assert int(idx.stat("path")) == 3
+        assert (idx.stat("passes"), idx.stat("qs_passes")) == (passes, qs), nq
+    idx.set_option("scan_max_auto", 4)
     idx.search(c_oracle.synth_block(0, 2, stream=1), 5)
-    assert int(idx.stat("path")) == 1            # tiny batch -> SIMT scan (fp32 128-bit loads)
-    idx.search(c_oracle.synth_block(0, 64, stream=1), 5)
-    assert int(idx.stat("path")) == 3            # dense contraction -> tcgen05
+    assert int(idx.stat("path")) == 1            # opt-in: tiny batches on the SIMT scan (fp32 128-bit loads)
     with pytest.raises(RuntimeError):
         idx.search(c_oracle.synth_block(0, 2, stream=1), 4096)   # k beyond the supported maximum
     with pytest.raises(AssertionError):
@@ -389,7 +450,7 @@ def test_packed_merge_and_overflow_marker():
     assert full.stat("merge_saw_overflow") == 0          # read-and-clear
 
 
-@pytest.mark.parametrize("path", ["umma_ts", "umma_ss", "scan_f32"])
+@pytest.mark.parametrize("path", ["umma_ts", "umma_qs", "scan_f32"])
 def test_overflowed_rows_carry_the_marker_until_rerun(path):
     """All-equal scores overflow every list: the asynchronous call leaves id -2 in the first slot of
     such rows; finish() re-runs them on the exact engine and the marker is gone."""
@@ -470,14 +531,14 @@ def test_shard_with_a_block_of_identical_rows_overflows_for_some_queries_only():
     np.testing.assert_array_equal(D.cpu().numpy(), Dr)
 
 
-@pytest.mark.parametrize("opts", [dict(bootstrap=1), dict(tighten_adaptive=0, tighten=400), dict(worst_case_margin=1),
-                                  dict(bootstrap=1, tighten=0)])
+@pytest.mark.parametrize("opts", [dict(), dict(bootstrap=1), dict(tighten_adaptive=0, tighten=400), dict(worst_case_margin=1),
+                                  dict(bootstrap=1, tighten=0), dict(center=0)])
 def test_schedule_options_of_the_tensor_engine_give_identical_results(opts, c1_data):
     """Every schedule of the TS engine (no bootstrap / dense bootstrap launch, adaptive / fixed refresher
     pacing, data-dependent / worst-case margin, geometric phases) returns the same bits: the schedule only
     decides how many candidates are looked at, the exact rescoring decides the result."""
     P, Q = c1_data
-    base = make_index("umma_ts", P)
+    base = make_index("umma_qs", P)
     D0, I0 = base.search(Q, 100)
     var = make_index("umma_ts", P, **opts)
     D1, I1 = var.search(Q, 100)
