@@ -40,8 +40,21 @@ BYTES_STREAMED_PER_ROW = D * 2      # bf16 shadow row read by the scoring kernel
 BYTES_ALGO_FP32_PER_ROW = D * 4     # SURVEY §8(d) B_algo = 3072 * N (fp32 collection read once)
 
 
+# BASELINE.json `configs` (C1..C5).  c4 is the headline metric and the default.
+CONFIGS = {
+    "c1": dict(rows=100_000, nq=173, k=100, name="configs[0]: 100k x 768, 173 queries, top-100"),
+    "c2": dict(rows=8_841_823, nq=173, k=1000, name="configs[1]: MS MARCO-sized 8.8M x 768, 173 queries, top-1000"),
+    "c3": dict(rows=11_100_000, nq=5571, k=100, name="configs[2]: OR-QuAC-sized 11.1M x 768, 5,571 queries, top-100"),
+    "c4": dict(rows=N_CAST, nq=NQ, k=TOPK, name="configs[3]: CAsT-sized 38.6M x 768, 173 queries, top-100"),
+    "c5": dict(rows=N_CAST, nq=16384, k=1000, name="configs[4]: batch sweep 1..16,384 queries x 38.6M x 768, top-1000"),
+}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS),
+                    help="BASELINE.json config: sets --rows/--nq/--k (c5 runs the batch-size sweep)")
+    ap.add_argument("--sweep-nq", default="1,2,4,8,16,32,64,128,173,256,512,1024,2048,4096,8192,16384")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -67,7 +80,24 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-oracle-check", action="store_true",
+                    help="skip the two oracle legs of the untimed check (full-size fp64 truth, overflow protocol)")
+    ap.add_argument("--inproc", type=int, default=1,
+                    help="N > 1: 1 = rank 0 also measures the single-process layout (one index over all GPUs, "
+                         "host buffers) after the main run and reports it under `inproc`")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0,
+                    help="length of the extra back-to-back run reported under `sustained` (0 = skip)")
+    args = ap.parse_args()
+    if args.config != "c4":
+        c = CONFIGS[args.config]
+        args.rows, args.nq, args.k = c["rows"], c["nq"], c["k"]
+    return args
+
+
+def metric_name(args):
+    if args.config == "c4" and args.rows == N_CAST and args.k == TOPK:
+        return METRIC
+    return f"exact top-{args.k} queries/sec over {args.rows / 1e6:.1f}M x 768"
 
 
 def measured_peaks():
@@ -256,12 +286,12 @@ def run_reference_arm(args):
     steps = min(args.steps, 10)
     cb, _ = cpu_reference_search(args.cpu_sample_rows, args.nq, args.k, steps, min(args.warmup, 3), args.rows)
     line = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 3),
         "ms_per_step": cb["ms_per_search_on_sample"] * args.rows / args.cpu_sample_rows,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CAsT-sized {args.rows}x768 fp32 collection, {args.nq} queries, top-{args.k} "
-                               f"(BASELINE.json configs[3]); CPU arm timed on a row sample and scaled"},
+        "config": {"workload": f"BASELINE.json {CONFIGS[args.config]['name']}: {args.rows}x768 fp32 collection, "
+                               f"{args.nq} queries, top-{args.k}; CPU arm timed on a row sample and scaled"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -348,6 +378,13 @@ def run_b2f_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    if args.config == "c5":
+        run_sweep(args, index, sharded, stream, barrier, dev, world, rank, n_local, data_norm, data_shift, exchange)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     Dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
     Id = torch.empty((nq, k), dtype=torch.int64, device=dev)
 
@@ -399,6 +436,33 @@ def run_b2f_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
 
+    # ---- sustained: the same step queued back to back for >= --sustain-seconds, so that the board's power
+    # governor is in steady state (the headline region at N = 8 lasts ~30 ms: a burst) ----
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_iter = int(min(max(args.sustain_seconds / max(dev_ms_max / args.steps * 1e-3, 1e-6), args.steps), 20000))
+        samp2 = ClockSampler(local_rank)
+        if rank == 0:
+            samp2.start()
+        barrier()
+        samp2.mark()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(n_iter):
+            step_device()
+        sharded.finish()
+        s1.record(stream)
+        barrier()
+        samp2.mark()
+        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sus_ms = float(ts.item())
+        sustained = {"seconds": round(sus_ms * 1e-3, 3), "steps": n_iter, "value": nq * n_iter / (sus_ms * 1e-3),
+                     "unit": UNIT, "ms_per_step": sus_ms / n_iter,
+                     "streamed_gbs_per_gpu": n_local * BYTES_STREAMED_PER_ROW * n_iter / (sus_ms * 1e-3) / 1e9,
+                     "clocks": samp2.stop() if rank == 0 else None}
+
     # ---- end-to-end timing through the public host-buffer API ----
     def step_e2e():
         if world == 1:
@@ -443,13 +507,13 @@ def run_b2f_arm(args):
         lanes_issued = (-(-min(nq, 256) // 16) * 16) if all_qs else 256
         achieved = rows_per_launch * BYTES_STREAMED_PER_ROW / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch > 0 else 0.0
         line = {
-            "metric": METRIC, "value": nq * args.steps / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
+            "metric": metric_name(args), "value": nq * args.steps / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16 prefilter + f64-accumulated exact rescoring (fp32 out)", "data": "synthetic",
             "config": {
-                "workload": f"CAsT-sized {args.rows}x768 collection (BASELINE.json configs[3]), {nq} queries, top-{k}, "
-                            f"row-sharded over {n_gpus} GPU(s), {n_local} rows on rank 0",
+                "workload": f"BASELINE.json {CONFIGS[args.config]['name']}: {args.rows}x768 collection, {nq} queries, "
+                            f"top-{k}, row-sharded over {n_gpus} GPU(s), {n_local} rows on rank 0",
                 "l2_policy": "inputs larger than L2 (>= 7 GB streamed per GPU per step vs 126 MB L2); no flush needed",
                 "engine_path": engine_path, "tensor_variant": args.variant, "data": args.data,
                 "passes_per_search": passes_per_search, "qs_passes_per_search": qs_passes,
@@ -480,6 +544,7 @@ def run_b2f_arm(args):
             "e2e": {"value": nq * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(q_host.nbytes) * n_gpus,
                     "d2h_bytes_per_step": int(nq * k * 12) * n_gpus, "ms_per_step": e2e_s / args.steps * 1e3},
+            "sustained": sustained,
             "per_rank": per_rank,
             "gpu_launches": int(stats_sum.tolist()[3]),
             "clocks": clocks,
@@ -488,10 +553,117 @@ def run_b2f_arm(args):
         if n_gpus == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference_search(min(args.cpu_sample_rows, args.rows), nq, k, 3, 1, args.rows)
             line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+    if world > 1 and args.inproc:
+        # The layout ConvDR's single-process driver actually uses (reference run_convdr_inference.py:324,
+        # :355-368): ONE process, one index object over all GPUs (faiss.index_cpu_to_gpu_multiple with
+        # shard=True), host buffers in and out.  Measured by rank 0 after the other ranks released their
+        # shards; they wait on a gloo barrier (a host wait: an NCCL barrier would spin a kernel on their GPUs).
+        ctl = dist.new_group(backend="gloo")
+        index.set_option("keep_on_reset", 0)
+        sharded.reset()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=ctl)
+        if rank == 0:
+            try:
+                line["inproc"] = inproc_measure(args, world, q_host, De, Ie)
+            except Exception as e:      # never lose the headline line to the extra measurement
+                line["inproc"] = {"error": repr(e)[:300]}
+        dist.barrier(group=ctl)
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_sweep(args, index, sharded, stream, barrier, dev, world, rank, n_local, data_norm, data_shift, exchange):
+    """BASELINE.json configs[4]: 1..16,384 queries against the resident 38.6M-row collection, top-1000 (what
+    data/gen_ranking_data.py:541-567 consumes after --top_n 1000): the memory- to compute-bound crossover.
+    Device-resident calls, CUDA events on the engine's stream, max over ranks, ~1 s per point."""
+    import torch
+    import torch.distributed as dist
+    from convdr_b200 import synth
+    peak, tensor_peak, peak_src = measured_peaks()
+    nqs = [int(x) for x in args.sweep_nq.split(",")]
+    k = args.k
+    q_all = torch.from_numpy(synth.block(0, max(nqs), seed=0, stream=1, norm=data_norm, mean_shift=data_shift)).to(dev)
+    points = []
+    for nq in nqs:
+        q = q_all[:nq].contiguous()
+        Dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        Id = torch.empty((nq, k), dtype=torch.int64, device=dev)
+
+        def timed(reps):
+            barrier()
+            index.reset_stats()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                sharded.search_async(q, k, Dd, Id)
+            clean = sharded.finish()
+            e1.record(stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / reps, clean
+
+        est, _ = timed(2)                                   # also the warm-up (workspace growth)
+        reps = int(min(max(1000.0 / max(est, 1e-3), 3), 200))   # ~1 s per point, the same on every rank
+        ms, clean = timed(reps)
+        passes = index.stat("passes") / reps
+        fb = sum(sharded.gather_floats(index.stat("fallback_queries")))
+        streamed = n_local * BYTES_STREAMED_PER_ROW * passes / (ms * 1e-3) / 1e9
+        useful_tf = 2.0 * nq * args.rows * D / (ms * 1e-3) / 1e12
+        points.append({"nq": nq, "ms_per_search": ms, "queries_per_s": nq / (ms * 1e-3), "passes": passes,
+                       "qs_passes": index.stat("qs_passes") / reps, "streamed_gbs_per_gpu": streamed,
+                       "hbm_frac": streamed / peak, "useful_tflops_all_gpus": useful_tf,
+                       "tensor_frac": useful_tf / (world * tensor_peak) if tensor_peak else None,
+                       "bound": "hbm" if streamed / peak >= useful_tf / (world * tensor_peak) else "tensor",
+                       "fallback_queries": fb, "clean": bool(clean), "reps": reps,
+                       "sorted_desc": bool((Dd[:, 1:] <= Dd[:, :-1]).all().item())})
+        if rank == 0:
+            print(json.dumps(points[-1]), file=sys.stderr, flush=True)
+    if rank == 0:
+        best = max(points, key=lambda p: p["queries_per_s"])
+        cross = next((p["nq"] for p in points if p["bound"] == "tensor"), None)
+        print(json.dumps({
+            "metric": metric_name(args) + " (batch-size sweep)", "value": best["queries_per_s"], "unit": UNIT,
+            "n_gpus": world, "steps": sum(p["reps"] for p in points), "warmup": 2 * len(points),
+            "ms_per_step": best["ms_per_search"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16 prefilter + f64-accumulated exact rescoring (fp32 out)", "data": "synthetic",
+            "config": {"workload": CONFIGS["c5"]["name"] + f", row-sharded over {world} GPU(s)", "data": args.data,
+                       "exchange": exchange, "peak_source": peak_src, "hbm_peak_gbs": peak,
+                       "tensor_peak_tflops_sustained": tensor_peak,
+                       "first_batch_size_where_the_tensor_fraction_exceeds_the_hbm_fraction": cross},
+            "sweep": points}), flush=True)
+
+
+def inproc_measure(args, n_dev, q_host, D_ref, I_ref):
+    """index.search(queries, k) with host buffers on ONE FlatIPIndex sharded over n_dev devices of this process."""
+    from convdr_b200 import FlatIPIndex
+    data_norm, data_shift = (28.0, 443) if args.data == "aniso" else (1.0, 0)
+    idx = FlatIPIndex(D, devices=list(range(n_dev)))
+    idx.set_option("path", args.path)
+    idx.set_option("umma_variant", args.variant)
+    idx.set_option("synth_mean_shift", data_shift)
+    cuts = [args.rows * i // n_dev for i in range(n_dev + 1)]
+    idx.reserve(max(cuts[i + 1] - cuts[i] for i in range(n_dev)))
+    for g in range(n_dev):
+        for a in range(cuts[g], cuts[g + 1], 1 << 22):
+            idx.add_synthetic(min(1 << 22, cuts[g + 1] - a), first_row=a, seed=0, stream=0, norm=data_norm,
+                              shard=g, id_base=a)
+    for _ in range(3):
+        Di, Ii = idx.search(q_host, args.k)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        Di, Ii = idx.search(q_host, args.k)
+    dt = (time.perf_counter() - t0) / args.steps
+    out = {"layout": f"one process, one index, {n_dev} shards, host buffers (index.search)", "value": args.nq / dt,
+           "unit": UNIT, "ms_per_step": dt * 1e3, "launches_per_search": idx.stat("launches"),
+           "equals_one_process_per_gpu_result": bool(np.array_equal(Ii, I_ref) and np.array_equal(Di, D_ref))}
+    idx.close()
+    return out
 
 
 def self_check(index, sharded, q_host, q_dev, Dd, Id, De, Ie, args, lo, hi, world, rank, dev):
@@ -518,7 +690,75 @@ def self_check(index, sharded, q_host, q_dev, Dd, Id, De, Ie, args, lo, hi, worl
     Ds, Is = sharded.search(qsub, args.k)
     index.set_option("path", args.path)
     out["tensor_engine_equals_simt_engine_4q"] = bool(torch.equal(Is, Id[:4]) and torch.equal(Ds, Dd[:4]))
+    if not args.no_oracle_check:
+        out.update(oracle_check_full_size(args, q_host, Dn, In, rank))
+        out.update(overflow_redo_check(args, world, rank, dev))
     return out
+
+
+def oracle_check_full_size(args, q_host, Dn, In, rank, n_queries: int = 16):
+    """Oracle parity AT THE BENCHMARK SIZE: the float64 ground truth of a query subset over
+    the WHOLE collection, regenerated on the host block by block (oracle/flat_ip_c.c `oracle_topk_synth_f64`,
+    all host threads; ~10-25 s for 38.6M rows), compared with the engine's (merged) answer by the parity
+    comparator of BASELINE.json (ids identical except at ties within 1e-5 relative; scores within 1e-5).
+    Unlike re-deriving the scores of the RETURNED rows, this detects a missed row.  Rank 0 computes it; every
+    rank holds the same merged (D, I).  Not timed."""
+    if rank != 0:
+        return {}
+    from oracle import c_oracle, flat_ip
+    from convdr_b200 import synth
+    data_norm, data_shift = (28.0, 443) if args.data == "aniso" else (1.0, 0)
+    sel = sorted(set(np.linspace(0, args.nq - 1, min(n_queries, args.nq)).astype(int).tolist()))
+    t0 = time.perf_counter()
+    Dt, It = c_oracle.topk_synth_f64(q_host[sel], args.k, 0, args.rows, seed=0, stream=0, norm=data_norm,
+                                     mean_shift=data_shift)
+    secs = time.perf_counter() - t0
+
+    def score_of(qi, ids):
+        r = synth.rows(np.asarray(ids).astype(np.uint64), seed=0, stream=0, norm=data_norm, mean_shift=data_shift)
+        return r.astype(np.float64) @ q_host[sel[qi]].astype(np.float64)
+
+    r = flat_ip.compare(Dn[sel], In[sel], Dt, It, score_of, rtol=1e-5)
+    return {"oracle_queries": len(sel), "oracle_rows": args.rows, "oracle_violations": r["violations"],
+            "oracle_exact_rows": r["exact_rows"], "oracle_tie_excused": r["tie_excused"],
+            "oracle_max_rel_score_err": r["max_rel_score_err"], "oracle_seconds": round(secs, 1),
+            "oracle_host_threads": os.cpu_count()}
+
+
+def overflow_redo_check(args, world, rank, dev):
+    """The overflow protocol at THIS world size: a small second collection whose last
+    5000 rows are identical (more than a candidate list holds) is sharded over the ranks; a 173-query
+    batch with two planted queries that rank those rows first makes the owning rank's lists overflow, the rows
+    travel with the in-band marker, every rank repeats the exchange after the owner's exact re-run
+    (convdr_b200/dist.py search_host's redo branch).  The result must equal the oracle's float64 truth."""
+    from convdr_b200 import FlatIPIndex
+    from convdr_b200.dist import ShardedFlatIP
+    from oracle import c_oracle, flat_ip
+    n = 60000
+    P = c_oracle.synth_block(0, n, seed=41)
+    P[55000:60000] = P[55000]
+    qh = c_oracle.synth_block(0, 173, seed=3, stream=1)
+    qh[7], qh[150] = P[55000], P[55000] * np.float32(0.5)
+    idx2 = FlatIPIndex(D, devices=[dev.index])
+    sh2 = ShardedFlatIP(index=idx2)
+    if world > 1 and args.exchange == "peer":
+        sh2.enable_peer_exchange(173, 100)
+    sh2.add(P)
+    idx2.reset_stats()
+    if world > 1:
+        Dh, Ih = sh2.search_host(qh, 100, device=dev)
+    else:
+        Dh, Ih = idx2.search(qh, 100)
+    reran = sum(sh2.gather_floats(idx2.stat("fallback_queries")))
+    ok = True
+    if rank == 0:
+        Dt, It = flat_ip.truth_fp64(qh, P, 100)
+        score_of = lambda qi, ids: qh[qi].astype(np.float64) @ P[ids].astype(np.float64).T
+        r = flat_ip.compare(Dh, Ih, Dt, It, score_of, rtol=1e-5)
+        ok = r["violations"] == 0 and bool(np.array_equal(Ih[7], It[7]) and np.array_equal(Ih[150], It[150]))
+    oks = sh2.gather_floats(1.0 if ok else 0.0)
+    idx2.close()
+    return {"overflow_redo_ok": bool(all(v > 0 for v in oks) and reran >= 2), "overflow_queries_rerun": reran}
 
 
 def main():

@@ -680,7 +680,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     const int pairs = std::min(S.max_pairs, te);
     {
       ProfScope ps(idx, S, 0);
-      umma_qs_score_select_kernel<<<2 * pairs, kUmmaThreads, qp.smem_bytes, s>>>(tmap_p, tmap_q, a);
+      umma_qs_score_select_kernel<<<2 * pairs, kQsThreads, qp.smem_bytes, s>>>(tmap_p, tmap_q, a);
     }
     CU_TRY(cudaGetLastError());
     st.score_rows += static_cast<double>(N);
@@ -1405,8 +1405,11 @@ static int xchg_push_and_merge(b2f_index* idx, int64_t nq, int k, float* D_dev, 
   }
   const int64_t i_off = round_up(nq * k * 4, 16);
   const int64_t n_vec = (i_off + nq * k * 8 + 15) / 16;
-  xchg_push_kernel<<<dim3(X.world, 4), 256, 0, S.stream>>>(reinterpret_cast<const uint4*>(X.stage), n_vec, peers, seq,
-                                                           X.counter);
+  // 4 blocks per destination for the headline part (208 KB); large batches (16,384 x 1000: 197 MB per part)
+  // get one block per 64 KB, up to 128 per destination, so the push runs at NVLink speed
+  const int gy = static_cast<int>(std::min<int64_t>(128, std::max<int64_t>(4, n_vec / 4096)));
+  xchg_push_kernel<<<dim3(X.world, gy), 256, 0, S.stream>>>(reinterpret_cast<const uint4*>(X.stage), n_vec, peers, seq,
+                                                            X.counter);
   CU_TRY(cudaGetLastError());
   idx->stats.launches += 1;
   if (!X.defer) return xchg_launch_merge(idx, seq, nq, k, D_dev, I_dev);

@@ -253,6 +253,53 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// "does any of these 32 scores reach the threshold?" as two interleaved predicate chains (setp.ge.or
+// accumulates into its predicate): one instruction per score instead of compare + select + or, and the mask
+// of WHICH scores hit is only built when some lane of the warp reports a hit.  The epilogue runs with one
+// warp per scheduler, so every instruction it saves is exposed latency saved (profiles/r02: the round-1
+// epilogue, not the tensor pipe, paced this kernel at full clocks).
+__device__ __forceinline__ bool any_ge32(const uint32_t* v, float tau) {
+  uint32_t r;
+  asm("{\n\t.reg .pred p, q;\n\t"
+      "setp.ge.f32 p, %1, %33;\n\t"
+      "setp.ge.f32 q, %2, %33;\n\t"
+      "setp.ge.or.f32 p, %3, %33, p;\n\t"
+      "setp.ge.or.f32 q, %4, %33, q;\n\t"
+      "setp.ge.or.f32 p, %5, %33, p;\n\t"
+      "setp.ge.or.f32 q, %6, %33, q;\n\t"
+      "setp.ge.or.f32 p, %7, %33, p;\n\t"
+      "setp.ge.or.f32 q, %8, %33, q;\n\t"
+      "setp.ge.or.f32 p, %9, %33, p;\n\t"
+      "setp.ge.or.f32 q, %10, %33, q;\n\t"
+      "setp.ge.or.f32 p, %11, %33, p;\n\t"
+      "setp.ge.or.f32 q, %12, %33, q;\n\t"
+      "setp.ge.or.f32 p, %13, %33, p;\n\t"
+      "setp.ge.or.f32 q, %14, %33, q;\n\t"
+      "setp.ge.or.f32 p, %15, %33, p;\n\t"
+      "setp.ge.or.f32 q, %16, %33, q;\n\t"
+      "setp.ge.or.f32 p, %17, %33, p;\n\t"
+      "setp.ge.or.f32 q, %18, %33, q;\n\t"
+      "setp.ge.or.f32 p, %19, %33, p;\n\t"
+      "setp.ge.or.f32 q, %20, %33, q;\n\t"
+      "setp.ge.or.f32 p, %21, %33, p;\n\t"
+      "setp.ge.or.f32 q, %22, %33, q;\n\t"
+      "setp.ge.or.f32 p, %23, %33, p;\n\t"
+      "setp.ge.or.f32 q, %24, %33, q;\n\t"
+      "setp.ge.or.f32 p, %25, %33, p;\n\t"
+      "setp.ge.or.f32 q, %26, %33, q;\n\t"
+      "setp.ge.or.f32 p, %27, %33, p;\n\t"
+      "setp.ge.or.f32 q, %28, %33, q;\n\t"
+      "setp.ge.or.f32 p, %29, %33, p;\n\t"
+      "setp.ge.or.f32 q, %30, %33, q;\n\t"
+      "setp.ge.or.f32 p, %31, %33, p;\n\t"
+      "setp.ge.or.f32 q, %32, %33, q;\n\t"
+      "or.pred p, p, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "f"(__uint_as_float(v[0])), "f"(__uint_as_float(v[1])), "f"(__uint_as_float(v[2])), "f"(__uint_as_float(v[3])), "f"(__uint_as_float(v[4])), "f"(__uint_as_float(v[5])), "f"(__uint_as_float(v[6])), "f"(__uint_as_float(v[7])), "f"(__uint_as_float(v[8])), "f"(__uint_as_float(v[9])), "f"(__uint_as_float(v[10])), "f"(__uint_as_float(v[11])), "f"(__uint_as_float(v[12])), "f"(__uint_as_float(v[13])), "f"(__uint_as_float(v[14])), "f"(__uint_as_float(v[15])), "f"(__uint_as_float(v[16])), "f"(__uint_as_float(v[17])), "f"(__uint_as_float(v[18])), "f"(__uint_as_float(v[19])), "f"(__uint_as_float(v[20])), "f"(__uint_as_float(v[21])), "f"(__uint_as_float(v[22])), "f"(__uint_as_float(v[23])), "f"(__uint_as_float(v[24])), "f"(__uint_as_float(v[25])), "f"(__uint_as_float(v[26])), "f"(__uint_as_float(v[27])), "f"(__uint_as_float(v[28])), "f"(__uint_as_float(v[29])), "f"(__uint_as_float(v[30])), "f"(__uint_as_float(v[31])), "f"(tau));
+  return r != 0u;
+}
+
 // ------------------------------------------------------------------------------------------
 // The kernel.  Grid = 2 * (number of CTA pairs), cluster (2,1,1), 256 threads:
 //   warp 0 lane 0 : TMA producer (both CTAs stream their own 64 rows of every tile)
@@ -441,6 +488,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
         // single column from TMEM (a dynamic register index would demote v[] to local memory).
 #pragma unroll
         for (int w = 0; w < kTileRows / 32; ++w) {
+          if (!__any_sync(0xffffffffu, any_ge32(v + 32 * w, tau))) continue;   // the common case: no lane hits
           uint32_t m = 0;
 #pragma unroll
           for (int c = 0; c < 32; ++c) m |= (__uint_as_float(v[32 * w + c]) >= tau) ? (1u << c) : 0u;

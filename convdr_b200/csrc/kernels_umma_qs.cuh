@@ -36,6 +36,8 @@ constexpr int kQsMaxCols = 256;                  // MMA N limit; two accumulator
 constexpr int kQsAccStride = 256;
 constexpr int kQsTailBytes = 4096;               // barriers, thresholds, counters, histogram bases
 constexpr int kQsSmemLimit = 232448;
+constexpr int kQsThreads = 384;                  // 4 service warps + 8 epilogue warps (two per TMEM lane quarter)
+constexpr int kQsEpiWarps = 8;
 
 struct UmmaQsArgs {
   int64_t n_rows;             // valid rows of the shard
@@ -92,16 +94,52 @@ __device__ __forceinline__ float4 lds_volatile_f4(uint32_t addr) {
   return r;
 }
 
+// "does any of these 16 scores reach its threshold?" as ONE predicate chain: setp.ge.or accumulates into the
+// same predicate, one instruction per score (the mask of WHICH scores hit is only built on the rare path).
+// With one or two warps per scheduler every instruction of the epilogue is exposed latency; the round-1
+// form (FSETP + SEL + IADD per score, then a warp reduction) made the epilogue — not the tensor pipe or
+// HBM — the bottleneck of this kernel (profiles/r02_ncu_qs_epilogue_bound.md).
+__device__ __forceinline__ bool any_ge16(const uint32_t (&v)[16], const float (&t)[16]) {
+  uint32_t r;
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.ge.f32 p, %1, %17;\n\t"
+      "setp.ge.or.f32 p, %2, %18, p;\n\t"
+      "setp.ge.or.f32 p, %3, %19, p;\n\t"
+      "setp.ge.or.f32 p, %4, %20, p;\n\t"
+      "setp.ge.or.f32 p, %5, %21, p;\n\t"
+      "setp.ge.or.f32 p, %6, %22, p;\n\t"
+      "setp.ge.or.f32 p, %7, %23, p;\n\t"
+      "setp.ge.or.f32 p, %8, %24, p;\n\t"
+      "setp.ge.or.f32 p, %9, %25, p;\n\t"
+      "setp.ge.or.f32 p, %10, %26, p;\n\t"
+      "setp.ge.or.f32 p, %11, %27, p;\n\t"
+      "setp.ge.or.f32 p, %12, %28, p;\n\t"
+      "setp.ge.or.f32 p, %13, %29, p;\n\t"
+      "setp.ge.or.f32 p, %14, %30, p;\n\t"
+      "setp.ge.or.f32 p, %15, %31, p;\n\t"
+      "setp.ge.or.f32 p, %16, %32, p;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "f"(__uint_as_float(v[0])), "f"(__uint_as_float(v[1])), "f"(__uint_as_float(v[2])), "f"(__uint_as_float(v[3])),
+        "f"(__uint_as_float(v[4])), "f"(__uint_as_float(v[5])), "f"(__uint_as_float(v[6])), "f"(__uint_as_float(v[7])),
+        "f"(__uint_as_float(v[8])), "f"(__uint_as_float(v[9])), "f"(__uint_as_float(v[10])), "f"(__uint_as_float(v[11])),
+        "f"(__uint_as_float(v[12])), "f"(__uint_as_float(v[13])), "f"(__uint_as_float(v[14])), "f"(__uint_as_float(v[15])),
+        "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]), "f"(t[4]), "f"(t[5]), "f"(t[6]), "f"(t[7]),
+        "f"(t[8]), "f"(t[9]), "f"(t[10]), "f"(t[11]), "f"(t[12]), "f"(t[13]), "f"(t[14]), "f"(t[15]));
+  return r != 0u;
+}
+
 // ------------------------------------------------------------------------------------------
-// Grid = 2 * (number of CTA pairs), cluster (2,1,1), 256 threads:
+// Grid = 2 * (number of CTA pairs), cluster (2,1,1), 384 threads:
 //   warp 0 lane 0 : passage producer (TMA; both CTAs stream their own 128 rows of every tile)
 //   warp 1        : MMA issuer (leader CTA only; one elected lane)
 //   warp 2        : TMEM allocation, then lane 0 = query producer (TMA from L2)
 //   warp 3        : refresher — raises the global thresholds from the hit histogram and refreshes the
 //                   CTA's shared-memory copy of all thresholds
-//   warps 4..7    : epilogue — TMEM lane quarter (warp % 4), one passage row per thread
+//   warps 4..11   : epilogue — TMEM lane quarter (warp % 4), one passage row per thread; the two warps of a
+//                   quarter take alternate 16-query chunks of the row
 // ------------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
     umma_qs_score_select_kernel(const __grid_constant__ CUtensorMap tmap_p,
                                 const __grid_constant__ CUtensorMap tmap_q, const UmmaQsArgs a) {
   extern __shared__ unsigned char umma_smem_raw[];
@@ -154,7 +192,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     mbar_init(bar_qres, 2);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);   // one multicast commit
-      mbar_init(bar_tempty + 8 * s, 8);  // 4 epilogue warps x 2 CTAs (leader's copy is the one used)
+      mbar_init(bar_tempty + 8 * s, 2 * kQsEpiWarps);  // epilogue warps x 2 CTAs (leader's copy is the one used)
     }
     fence_mbar_init();
   }
@@ -164,7 +202,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 0) *epi_done_s = 0;
-  for (int i = threadIdx.x; i < kQsMaxCols; i += kUmmaThreads) {
+  for (int i = threadIdx.x; i < kQsMaxCols; i += kQsThreads) {
     tau_s[i] = (i < a.nq) ? a.tau[i] : INFINITY;     // padded query columns never hit
     cnt_s[i] = 0;
     hkey0_s[i] = (i < a.nq) ? a.hkey0[i] : 0xffffffffu;
@@ -255,7 +293,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     }
   } else if (warp >= 4) {
     // ===================== epilogue: filter + append =====================
-    const int ew = warp & 3;
+    const int ew = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;        // which of the alternating 16-query chunks
     const uint32_t tempty_leader0 = mapa_u32(bar_tempty, 0);
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int area = static_cast<int>(blockIdx.x);    // this CTA's private area in every query's list
@@ -291,7 +330,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
       const bool row_ok = row64 < a.n_rows;
       const uint32_t row = static_cast<uint32_t>(row64);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * kQsAccStride;
-      for (int c0 = 0; c0 < a.n_cols; c0 += 16) {
+      for (int c0 = 16 * half; c0 < a.n_cols; c0 += 32) {
         uint32_t v[16];
         tmem_ld_x16(taddr + c0, v);
         // thresholds of these 16 queries (volatile: the refresher warp rewrites them while we run)
@@ -302,12 +341,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
           t[4 * u] = f.x; t[4 * u + 1] = f.y; t[4 * u + 2] = f.z; t[4 * u + 3] = f.w;
         }
         tmem_ld_wait();
-        uint32_t m = 0;
+        const bool mine = row_ok && any_ge16(v, t);
+        if (__any_sync(0xffffffffu, mine)) {
+          // some row of this warp reached a threshold of this chunk: now build the per-lane hit mask
+          uint32_t m = 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) m |= (__uint_as_float(v[j]) >= t[j]) ? (1u << j) : 0u;
-        if (!row_ok) m = 0;
-        uint32_t any = __reduce_or_sync(0xffffffffu, m);
-        if (any) {
+          for (int j = 0; j < 16; ++j) m |= (__uint_as_float(v[j]) >= t[j]) ? (1u << j) : 0u;
+          if (!row_ok) m = 0;
+          uint32_t any = __reduce_or_sync(0xffffffffu, m);
           if (__popc(any) > 4) {
             // busy chunk (loose thresholds, the first tiles of a pass): unrolled, v[] stays in registers
 #pragma unroll
@@ -328,9 +369,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * as);
     }
-    // all four epilogue warps are done appending: publish the per-area counts
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int q = threadIdx.x - 128; q < a.nq; q += 128) {
+    // all epilogue warps are done appending: publish the per-area counts
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int q = threadIdx.x - 128; q < a.nq; q += 32 * kQsEpiWarps) {
       const int c = cnt_s[q];
       a.cnt2[q * a.n_areas + area] = min(c, a.cap_p);
       if (c > a.cap_p) a.ovf[q] = 1;
@@ -345,7 +386,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     // where the epilogue threads (one passage row each, all queries) read them.
     float last[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     const long long t_start = clock64();
-    while (*epi_done_s < 4) {
+    while (*epi_done_s < kQsEpiWarps) {
       int qi = 0;
       if (a.tighten) {
         for (int q = blockIdx.x; q < a.nq; q += gridDim.x, ++qi) {

@@ -1,6 +1,8 @@
 """Worker of tests/test_gpu_parity.py::test_peer_memory_exchange_equals_nccl_exchange (2+ GPUs):
 one process per GPU; the same sharded searches through ncclAllGather + merge and through the engine's
-peer-memory exchange kernels must give bit-identical results, equal to a single index over everything."""
+peer-memory exchange kernels must give bit-identical results, equal to a single index over everything
+AND to the oracle's float64 ground truth (ids identical; ties cannot occur outside the planted block,
+where the oracle's (score desc, index asc) order is the engine's total order too)."""
 import os
 
 import numpy as np
@@ -9,6 +11,20 @@ import torch.distributed as dist
 
 from convdr_b200 import FlatIPIndex, synth
 from convdr_b200.dist import ShardedFlatIP
+from oracle import flat_ip
+
+RTOL_TRUTH = 1e-6
+
+
+def check_truth(D, I, P, q, k):
+    """Sharded result vs the oracle's fp64 truth over the whole collection (reference: FAISS IndexShards over
+    all GPUs, drivers/run_convdr_inference.py:355-368, must equal one flat index)."""
+    Dt, It = flat_ip.truth_fp64(q, P, k)
+    score_of = lambda qi, ids: q[qi].astype(np.float64) @ P[ids].astype(np.float64).T
+    r = flat_ip.compare(D, I, Dt, It, score_of, rtol=1e-5)
+    assert r["violations"] == 0, r
+    rel = np.abs(D.astype(np.float64) - Dt) / np.maximum(np.abs(Dt), 1e-30)
+    assert rel.max() <= RTOL_TRUTH, rel.max()
 
 
 def main():
@@ -18,7 +34,8 @@ def main():
     dist.init_process_group("nccl", init_method="env://", device_id=dev)
     n = 60000
     P = synth.block(0, n, seed=41)
-    P[50000:51500] = P[50000]                       # 1500 identical rows (> the survivor capacity): overflow on the owning rank
+    P[55000:60000] = P[55000]                       # 5000 identical rows (> the survivor capacity of 4096) at the end of
+                                                    # the collection: the LAST rank's list overflows for queries that rank them high
     idx = FlatIPIndex(768, devices=[dev.index])
     sh = ShardedFlatIP(index=idx)
     sh.add(P)
@@ -36,9 +53,10 @@ def main():
             Df, If = full.search(q.cpu().numpy(), k)
             np.testing.assert_array_equal(out[-1][1], If)
             np.testing.assert_array_equal(out[-1][0], Df)
+            check_truth(out[-1][0], out[-1][1], P, q.cpu().numpy(), k)
         # a query equal to the duplicated row: every duplicate ties, the owning rank's list overflows,
         # the marker travels, every rank repeats the exchange after the local re-run
-        q = torch.from_numpy(np.ascontiguousarray(P[50000:50008])).to(dev)   # 8 queries: tensor engine
+        q = torch.from_numpy(np.ascontiguousarray(P[55000:55008])).to(dev)   # 8 queries: tensor engine
         idx.reset_stats()
         D, I = sh.search(q, 50)
         assert idx.stat("fallback_queries") == (8 if rank == world - 1 else 0)
@@ -46,6 +64,8 @@ def main():
         np.testing.assert_array_equal(I.cpu().numpy(), If)
         np.testing.assert_array_equal(D.cpu().numpy(), Df)
         out.append((D.cpu().numpy(), I.cpu().numpy()))
+        Dt, It = flat_ip.truth_fp64(q.cpu().numpy(), P, 50)      # 5000 exact ties: (score desc, index asc) on both sides
+        np.testing.assert_array_equal(I.cpu().numpy(), It)
         # queued searches, one settle
         q = torch.from_numpy(synth.block(0, 50, seed=9, stream=1)).to(dev)
         outs = [(torch.empty((50, 20), dtype=torch.float32, device=dev), torch.empty((50, 20), dtype=torch.int64, device=dev))
@@ -57,13 +77,19 @@ def main():
         for D, I in outs:
             np.testing.assert_array_equal(I.cpu().numpy(), If)
             np.testing.assert_array_equal(D.cpu().numpy(), Df)
-        # host-buffer path (one host wait; the 173-query batch contains two overflowing queries -> redo branch)
+        # host-buffer path (one host wait; the 173-query batch contains two planted overflowing queries -> redo branch)
         for nq, kk, seed in ((37, 100, 2), (173, 100, 3), (37, 100, 2)):
             qh = synth.block(0, nq, seed=seed, stream=1)
+            if nq == 173:
+                qh[7], qh[150] = P[55000], P[55000] * np.float32(0.5)
+                idx.reset_stats()
             Dh, Ih = sh.search_host(qh, kk, device=dev)
             Df, If = full.search(qh, kk)
             np.testing.assert_array_equal(Ih, If)
             np.testing.assert_array_equal(Dh, Df)
+            check_truth(Dh, Ih, P, qh, kk)
+            if nq == 173:    # the redo branch really ran: the owning rank re-ran at least the two planted queries
+                assert (idx.stat("fallback_queries") >= 2) == (rank == world - 1), idx.stat("fallback_queries")
         results[mode] = out
     for (Da, Ia), (Db, Ib) in zip(results["nccl"], results["peer"]):
         np.testing.assert_array_equal(Ia, Ib)

@@ -505,18 +505,19 @@ def test_peer_memory_exchange_equals_nccl_exchange(gpu_count):
 
 
 def test_shard_with_a_block_of_identical_rows_overflows_for_some_queries_only():
-    """1500 identical rows (> the survivor capacity) inside a shard with explicit ids: the few queries
+    """5000 identical rows (> the survivor capacity of 4096) inside a shard with explicit ids: the few queries
     that rank them high overflow, carry the marker after the asynchronous call, and are settled by
     finish(); all others are untouched.  (The data of the 2-GPU exchange test, one shard of it.)"""
     import torch
     P = c_oracle.synth_block(0, 60000, seed=41)
-    P[50000:51500] = P[50000]
+    P[55000:60000] = P[55000]
     ids = np.arange(30000, 60000, dtype=np.int64)
     idx = make_index("auto")
     idx.add_with_ids(P[30000:], ids)
     ref = make_index("scan_exact")
     ref.add_with_ids(P[30000:], ids)
     Qh = c_oracle.synth_block(0, 173, seed=3, stream=1)
+    Qh[5], Qh[100] = P[55000], P[55000] * np.float32(0.5)     # these two rank the identical rows first: overflow
     q = torch.from_numpy(Qh).cuda()
     D = torch.empty((173, 100), dtype=torch.float32, device="cuda")
     I = torch.empty((173, 100), dtype=torch.int64, device="cuda")
@@ -524,6 +525,7 @@ def test_shard_with_a_block_of_identical_rows_overflows_for_some_queries_only():
     idx.search_device_async(q, 100, D, I)
     torch.cuda.synchronize()
     marked = int((I[:, 0] == -2).sum().item())
+    assert 2 <= marked < 173
     idx.finish()
     assert idx.stat("fallback_queries") == marked
     Dr, Ir = ref.search(Qh, 100)
