@@ -143,6 +143,7 @@ struct Workspace {
 
 struct Stats {
   double launches = 0, phases = 0, candidates = 0, fallback_queries = 0, path = 0, passes = 0, qs_passes = 0;
+  double ovf_area = 0, ovf_survivors = 0;   // why queries fell back: private area too small / too many rows within the margin
   double score_ms = 0, score_launches = 0, score_rows = 0, select_ms = 0, xchg_ms = 0;
 };
 
@@ -280,7 +281,10 @@ struct b2f_index {
   int umma_variant = 0;   // 0 auto (QS up to qs_max_q queries per pass, TS above), 1 QS with every query K-block
                           // resident in shared memory (the round-1 "SS" layout), 2 TS (queries in TMEM), 3 QS
   int qs_max_q = 208;     // AUTO: passes of up to this many queries take the QS variant (MMA N = nq rounded to 16)
-  int qs_resident_kb = 0; // QS: query K-blocks kept resident in shared memory (0..12); the rest streams from L2
+  int qs_resident_kb = 12; // QS: query K-blocks kept resident in shared memory (0..12; lowered automatically when the
+                          // batch is too large to leave a passage ring of 4 stages); the rest streams from L2.  Measured
+                          // (profiles/r02): fully resident wins for <= 208 queries — the re-read query bytes cost more
+                          // L2->SM bandwidth and power than the deeper passage ring gains
   int qs_q_stages = 3;    // QS: depth of the query ring
   int center = 1;         // subtract the collection mean (first rows of the first add) before the bf16 rounding
   int synth_mean_shift = 0;  // b2f_add_synthetic: integer shift of every component along a fixed sign vector
@@ -678,6 +682,12 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     a.tau = W.tau; a.ovf = W.ovf; a.err = W.err; a.tighten = idx->tighten; a.tighten_adaptive = idx->tighten_adaptive;
     a.k = k; a.margin = W.margin; a.hist = W.hist; a.hkey0 = W.hkey0; a.hshift = W.hshift;
     const int pairs = std::min(S.max_pairs, te);
+    // First tile of every CTA: `dense_quarters` of its four 32-row quarters pass unfiltered (they seed the
+    // histogram: 2 * pairs * 32 rows per quarter, about half of which score above the histogram floor), the
+    // other quarters wait until every query has a threshold (bounded: first_wait_cycles).  Shards too small
+    // to fill the first tiles do not wait.
+    a.dense_quarters = std::min(4, std::max(1, (4 * k + 2 * pairs * 32 - 1) / (2 * pairs * 32)));
+    a.first_wait_cycles = (idx->tighten && N >= 4ll * pairs * kQsTileRows && a.dense_quarters < 4) ? 100000 : 0;
     {
       ProfScope ps(idx, S, 0);
       umma_qs_score_select_kernel<<<2 * pairs, kQsThreads, qp.smem_bytes, s>>>(tmap_p, tmap_q, a);
@@ -888,7 +898,11 @@ int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k,
   const int* flags = W.ovf_host + static_cast<size_t>(slot) * W.nq_cap;
   std::vector<int64_t> bad;
   for (int64_t q = 0; q < nq; ++q)
-    if (flags[q]) bad.push_back(q);
+    if (flags[q]) {
+      bad.push_back(q);
+      if (flags[q] & 1) S.stats.ovf_area += 1;
+      if (flags[q] & 2) S.stats.ovf_survivors += 1;
+    }
   if (bad.empty()) return B2F_OK;
   if (reran) *reran = true;
   S.stats.fallback_queries += static_cast<double>(bad.size());
@@ -1593,6 +1607,7 @@ int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
   for (const Shard& S : idx->shards) {
     s.launches += S.stats.launches; s.phases += S.stats.phases; s.candidates += S.stats.candidates;
     s.fallback_queries += S.stats.fallback_queries; s.passes += S.stats.passes; s.qs_passes += S.stats.qs_passes; s.score_ms += S.stats.score_ms;
+    s.ovf_area += S.stats.ovf_area; s.ovf_survivors += S.stats.ovf_survivors;
     s.score_launches += S.stats.score_launches; s.score_rows += S.stats.score_rows; s.select_ms += S.stats.select_ms;
     s.xchg_ms += S.stats.xchg_ms;
   }
@@ -1609,6 +1624,8 @@ int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
   else if (k == "path") *out = s.path;
   else if (k == "passes") *out = s.passes;
   else if (k == "qs_passes") *out = s.qs_passes;
+  else if (k == "overflow_area") *out = s.ovf_area;
+  else if (k == "overflow_survivors") *out = s.ovf_survivors;
   else if (k == "score_ms") *out = s.score_ms;
   else if (k == "score_launches") *out = s.score_launches;
   else if (k == "score_rows") *out = s.score_rows;

@@ -658,8 +658,11 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
     I_out[static_cast<int64_t>(q) * out_stride + i] = id;
   }
   if (tid == 0) {
-    const bool bad = ovf[q] != 0 || m2_all > S;
-    if (ovf_out) ovf_out[q] = bad ? 1 : 0;
+    // flag bits: 1 = a private area was too small (thresholds came late), 2 = more rows within the error
+    // margin of the k-th score than the survivor buffer holds (ties / unresolvable score distribution)
+    const int kind = (ovf[q] != 0 ? 1 : 0) | (m2_all > S ? 2 : 0);
+    const bool bad = kind != 0;
+    if (ovf_out) ovf_out[q] = kind;
     // in-band marker for the sharded layout: a row whose list overflowed carries id -2 in its first
     // slot until the exact engine has re-run it; merge_kernel reports it to every rank
     if (bad) I_out[static_cast<int64_t>(q) * out_stride] = -2;

@@ -36,8 +36,10 @@ constexpr int kQsMaxCols = 256;                  // MMA N limit; two accumulator
 constexpr int kQsAccStride = 256;
 constexpr int kQsTailBytes = 4096;               // barriers, thresholds, counters, histogram bases
 constexpr int kQsSmemLimit = 232448;
-constexpr int kQsThreads = 384;                  // 4 service warps + 8 epilogue warps (two per TMEM lane quarter)
+constexpr int kQsThreads = 416;                  // 4 service warps + 8 epilogue warps (two per TMEM lane quarter) + refresher
 constexpr int kQsEpiWarps = 8;
+constexpr int kQsRefresherWarp = 12;             // the highest warp id: the scheduler prefers it over the epilogue
+                                                 // warps of its quarter, so thresholds never wait behind appends
 
 struct UmmaQsArgs {
   int64_t n_rows;             // valid rows of the shard
@@ -62,6 +64,8 @@ struct UmmaQsArgs {
   unsigned int* hist;         // [nq][kHistStride]
   const uint32_t* hkey0;      // [nq]
   const int* hshift;          // [nq]
+  int dense_quarters;         // first tile of a CTA: lane quarters [0, dense_quarters) pass unfiltered
+  int first_wait_cycles;      // the other quarters wait this long at most for every threshold to exist (0: no wait)
 };
 
 struct QsPlan { int a_stages, q_stages, resident_kb, smem_bytes; };
@@ -134,10 +138,11 @@ __device__ __forceinline__ bool any_ge16(const uint32_t (&v)[16], const float (&
 //   warp 0 lane 0 : passage producer (TMA; both CTAs stream their own 128 rows of every tile)
 //   warp 1        : MMA issuer (leader CTA only; one elected lane)
 //   warp 2        : TMEM allocation, then lane 0 = query producer (TMA from L2)
-//   warp 3        : refresher — raises the global thresholds from the hit histogram and refreshes the
-//                   CTA's shared-memory copy of all thresholds
+//   warp 3        : idle
 //   warps 4..11   : epilogue — TMEM lane quarter (warp % 4), one passage row per thread; the two warps of a
 //                   quarter take alternate 16-query chunks of the row
+//   warp 12       : refresher — raises the global thresholds from the hit histogram and refreshes the
+//                   CTA's shared-memory copy of all thresholds
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
     umma_qs_score_select_kernel(const __grid_constant__ CUtensorMap tmap_p,
@@ -165,6 +170,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
   unsigned char* tail_ptr = base_ptr + tail_off;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail_ptr + 16 * kQsMaxAStages + 16 * kQsMaxQStages + 8 + 32);
   volatile int* epi_done_s = reinterpret_cast<volatile int*>(tmem_ptr_s + 1);
+  volatile int* tau_ready_s = reinterpret_cast<volatile int*>(tmem_ptr_s + 2);   // every query has a finite threshold
   float* tau_s = reinterpret_cast<float*>(tail_ptr + 512);               // [kQsMaxCols]
   int* cnt_s = reinterpret_cast<int*>(tail_ptr + 512 + 1024);            // [kQsMaxCols]
   uint32_t* hkey0_s = reinterpret_cast<uint32_t*>(tail_ptr + 512 + 2048);  // [kQsMaxCols]
@@ -201,7 +207,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
                  ::"r"(smem_u32(tmem_ptr_s)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x == 0) *epi_done_s = 0;
+  if (threadIdx.x == 0) { *epi_done_s = 0; *tau_ready_s = 0; }
   for (int i = threadIdx.x; i < kQsMaxCols; i += kQsThreads) {
     tau_s[i] = (i < a.nq) ? a.tau[i] : INFINITY;     // padded query columns never hit
     cnt_s[i] = 0;
@@ -326,6 +332,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       mbar_wait(bar_tfull + 8 * as, aph, a.err);
       tc_fence_after();
+      if (it == 0 && ew >= a.dense_quarters && a.first_wait_cycles > 0) {
+        // Thresholds start at -inf.  Only the first quarter(s) of a CTA's first tile pass unfiltered — enough
+        // rows over all CTAs to place every query's threshold; the other quarters wait for the refresher's
+        // "every query has a threshold" flag instead of appending 96 more rows x all queries that the final
+        // selection would throw away again.  Bounded wait: a query whose scores never reach the histogram
+        // keeps tau = -inf, which is slow (its lists overflow and the query is re-run) but never wrong.
+        const long long t0 = clock64();
+        while (*tau_ready_s == 0 && clock64() - t0 < a.first_wait_cycles) __nanosleep(256);
+      }
       const int64_t row64 = static_cast<int64_t>(tile) * kQsTileRows + cta_rank * kQsTileRowsCta + ew * 32 + lane;
       const bool row_ok = row64 < a.n_rows;
       const uint32_t row = static_cast<uint32_t>(row64);
@@ -378,7 +393,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
     }
     __syncwarp();
     if (lane == 0) atomicAdd(const_cast<int*>(epi_done_s), 1);
-  } else if (warp == 3) {
+  } else if (warp == kQsRefresherWarp) {
     // ===================== refresher: in-kernel threshold tightening =====================
     // Same scheme as the TS variant (kernels_umma.cuh): for the queries assigned to this CTA, read the
     // histogram of hits, find the highest bucket b with >= k hits at or above it and publish
@@ -435,12 +450,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
         }
       }
       // thresholds published by every CTA -> this CTA's shared memory (they only rise)
+      bool all_finite = true;
       for (int i = lane; i < a.nq; i += 32) {
         const float t = *reinterpret_cast<volatile float*>(a.tau + i);
         if (t > tau_s[i]) *reinterpret_cast<volatile float*>(tau_s + i) = t;
+        all_finite = all_finite && (t > -INFINITY);
       }
+      if (__all_sync(0xffffffffu, all_finite) && lane == 0) *tau_ready_s = 1;
       unsigned int pause = static_cast<unsigned int>(a.tighten > 0 ? a.tighten : 2000);
-      if (a.tighten_adaptive) {
+      if (*tau_ready_s == 0) pause = 500;     // start of the pass: epilogue warps are waiting for the first thresholds
+      else if (a.tighten_adaptive) {
         const long long age_ns = (clock64() - t_start) >> 1;     // cycles -> ns at ~2 GHz; only a pacing hint
         pause = static_cast<unsigned int>(min(max(static_cast<long long>(pause), age_ns >> 2), 50000ll));
       }
