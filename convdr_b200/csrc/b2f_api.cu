@@ -25,6 +25,11 @@
 #include <cstring>
 #include <string>
 #include <type_traits>
+#include <atomic>
+#include <chrono>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <vector>
 
 #include "common.cuh"
@@ -269,6 +274,7 @@ struct b2f_index {
     struct Deferred { bool valid = false; unsigned int seq = 0; int64_t nq = 0; int k = 0; float* D = nullptr; int64_t* I = nullptr; } deferred;
   } xchg;
   int64_t ntotal = 0;
+  std::mutex ntotal_mutex;     // b2f_add_flat_file may run on several shards at once (one host thread each)
   // options
   int path = B2F_PATH_AUTO;
   int shadow = 1;
@@ -1643,3 +1649,182 @@ int b2f_get_stat(const b2f_index* idx, const char* key, double* out) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Resident load of a flat shard file: what replaces `pickle.load` + `index.add` of the
+// reference's block loop (drivers/run_convdr_inference.py:161-180), whose 118 GB of unpickling + pageable
+// H2D per run is its real wall-clock cost.  Reader threads pread() fixed-size pieces of the row region into a
+// ring of pinned staging buffers; the calling thread queues one cudaMemcpyAsync per piece as soon as it is
+// filled, two copies in flight, so file reads (page cache or disk), PCIe and — at the end — the ingest kernel
+// (bf16 shadow + bounds, ~1 ms per million rows) overlap.  One call per shard; calls for different shards may
+// run concurrently from different host threads (every GPU has its own PCIe link).
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+#pragma pack(push, 1)
+struct FlatHeader {              // convdr_b200/blocks.py `_HEADER` = "<8sIIQIQQ"
+  char magic[8];
+  uint32_t version, d;
+  uint64_t n;
+  uint32_t dtype;
+  uint64_t rows_off, ids_off;
+};
+#pragma pack(pop)
+static_assert(sizeof(FlatHeader) == 44, "header layout is part of the file format");
+
+bool pread_all(int fd, void* dst, size_t bytes, off_t off) {
+  char* p = static_cast<char*>(dst);
+  while (bytes > 0) {
+    const ssize_t r = pread(fd, p, bytes, off);
+    if (r <= 0) return false;
+    p += r; off += r; bytes -= static_cast<size_t>(r);
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" int b2f_add_flat_file(b2f_index* idx, int shard, const char* path, int n_threads, double* seconds_out,
+                                 double* gbytes_out) {
+  if (!idx || !path || shard < 0 || shard >= static_cast<int>(idx->shards.size()))
+    return fail(B2F_ERR_INVALID, "bad add_flat_file arguments");
+  B2F_TRY(settle_pending(idx));
+  Shard& S = idx->shards[shard];
+  if (S.n > 0 && !S.has_ids) return fail(B2F_ERR_INVALID, "cannot mix add() and labelled rows on a non-empty shard");
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(B2F_ERR_INVALID, std::string("cannot open ") + path);
+  struct FdGuard { int fd; ~FdGuard() { close(fd); } } guard{fd};
+  FlatHeader h;
+  struct stat st;
+  if (fstat(fd, &st) != 0 || !pread_all(fd, &h, sizeof(h), 0) || std::memcmp(h.magic, "B2FSHARD", 8) != 0)
+    return fail(B2F_ERR_INVALID, std::string(path) + ": not a b2f flat shard");
+  if (h.version != 1 || h.dtype != 0 || h.d != static_cast<uint32_t>(kD))
+    return fail(B2F_ERR_INVALID, std::string(path) + ": unsupported version / dtype / dimension");
+  const int64_t n = static_cast<int64_t>(h.n);
+  if (h.rows_off + static_cast<uint64_t>(n) * kD * 4 > h.ids_off || h.ids_off + static_cast<uint64_t>(n) * 8 > static_cast<uint64_t>(st.st_size))
+    return fail(B2F_ERR_INVALID, std::string(path) + ": file shorter than its header claims");
+  if (seconds_out) *seconds_out = 0.0;
+  if (gbytes_out) *gbytes_out = 0.0;
+  if (n == 0) return B2F_OK;
+  if (S.n + n >= 0xfffffff0ll) return fail(B2F_ERR_INVALID, "a shard holds at most 2^32-16 rows");
+  CU_TRY(cudaSetDevice(S.dev));
+  CU_TRY(cudaStreamSynchronize(S.stream));
+  if (!S.has_ids) {
+    S.has_ids = true;
+    if (S.cap > 0 && !S.idmap) B2F_TRY(dev_alloc(&S.idmap, static_cast<size_t>(S.cap)));
+  }
+  B2F_TRY(ensure_capacity(idx, S, S.n + n));
+  const auto t_begin = std::chrono::steady_clock::now();
+
+  constexpr int64_t kPieceRows = 8192;                     // 24 MB per piece
+  constexpr int kBufs = 6;
+  const size_t piece_bytes = static_cast<size_t>(kPieceRows) * kD * 4;
+  const int64_t n_pieces = (n + kPieceRows - 1) / kPieceRows;
+  const int T = std::max(1, std::min(n_threads > 0 ? n_threads : 4, 16));
+  char* bufs[kBufs] = {nullptr};
+  cudaEvent_t evs[kBufs] = {nullptr};
+  int rc = B2F_OK;
+  for (int b = 0; b < kBufs && rc == B2F_OK; ++b) {
+    if (cudaMallocHost(reinterpret_cast<void**>(&bufs[b]), piece_bytes) != cudaSuccess ||
+        cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming) != cudaSuccess) {
+      (void)cudaGetLastError();
+      rc = fail(B2F_ERR_OOM, "pinned staging allocation failed");
+    }
+  }
+  // piece state: filled[i] set by its reader, released[i] set by this thread once the copy out of the buffer is done
+  std::vector<std::atomic<int>> filled(static_cast<size_t>(n_pieces)), released(static_cast<size_t>(n_pieces));
+  for (auto& a : filled) a.store(0);
+  for (auto& a : released) a.store(0);
+  std::atomic<int> failed{0};
+  std::mutex m;
+  std::condition_variable cv;
+  std::vector<std::thread> readers;
+  if (rc == B2F_OK) {
+    for (int t = 0; t < T; ++t) {
+      readers.emplace_back([&, t] {
+        for (int64_t i = t; i < n_pieces && !failed.load(); i += T) {
+          if (i >= kBufs) {   // the buffer is reused: wait until piece i - kBufs has left it
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [&] { return released[static_cast<size_t>(i - kBufs)].load() || failed.load(); });
+            if (failed.load()) return;
+          }
+          const int64_t r0 = i * kPieceRows, rows = std::min<int64_t>(kPieceRows, n - r0);
+          if (!pread_all(fd, bufs[i % kBufs], static_cast<size_t>(rows) * kD * 4,
+                         static_cast<off_t>(h.rows_off + static_cast<uint64_t>(r0) * kD * 4)))
+            failed.store(1);
+          { std::lock_guard<std::mutex> lk(m); filled[static_cast<size_t>(i)].store(1); }
+          cv.notify_all();
+        }
+      });
+    }
+    // labels: one read, one copy (8 bytes per row)
+    std::vector<int64_t> ids(static_cast<size_t>(n));
+    if (!pread_all(fd, ids.data(), static_cast<size_t>(n) * 8, static_cast<off_t>(h.ids_off))) failed.store(1);
+    if (!failed.load() &&
+        cudaMemcpyAsync(S.idmap + S.n, ids.data(), static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, S.stream) != cudaSuccess)
+      failed.store(2);
+    if (!failed.load() && cudaStreamSynchronize(S.stream) != cudaSuccess) failed.store(2);   // `ids` is pageable and local
+    for (int64_t i = 0; i < n_pieces && !failed.load(); ++i) {
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return filled[static_cast<size_t>(i)].load() || failed.load(); });
+      }
+      if (failed.load()) break;
+      const int64_t r0 = i * kPieceRows, rows = std::min<int64_t>(kPieceRows, n - r0);
+      if (cudaMemcpyAsync(S.x32 + (S.n + r0) * kD, bufs[i % kBufs], static_cast<size_t>(rows) * kD * 4,
+                          cudaMemcpyHostToDevice, S.stream) != cudaSuccess ||
+          cudaEventRecord(evs[i % kBufs], S.stream) != cudaSuccess) {
+        failed.store(2);
+        break;
+      }
+      if (i >= 2) {   // two copies stay queued; the one before them has finished or is about to
+        if (cudaEventSynchronize(evs[(i - 2) % kBufs]) != cudaSuccess) { failed.store(2); break; }
+        { std::lock_guard<std::mutex> lk(m); released[static_cast<size_t>(i - 2)].store(1); }
+        cv.notify_all();
+      }
+    }
+    if (cudaStreamSynchronize(S.stream) != cudaSuccess && !failed.load()) failed.store(2);
+    {
+      std::lock_guard<std::mutex> lk(m);
+      for (auto& a : released) a.store(1);
+      if (failed.load() == 0) { /* nothing */ }
+    }
+    cv.notify_all();
+    for (std::thread& th : readers) th.join();
+    if (failed.load() == 1) rc = fail(B2F_ERR_INVALID, std::string(path) + ": read error");
+    else if (failed.load() == 2) { (void)cudaGetLastError(); rc = fail(B2F_ERR_CUDA, "copy of a staged piece failed"); }
+  }
+  for (int b = 0; b < kBufs; ++b) {
+    if (bufs[b]) cudaFreeHost(bufs[b]);
+    if (evs[b]) cudaEventDestroy(evs[b]);
+  }
+  if (rc != B2F_OK) return rc;
+  B2F_TRY(ingest_rows(idx, S, n));
+  S.n += n;
+  CU_TRY(cudaStreamSynchronize(S.stream));
+  {
+    std::lock_guard<std::mutex> lk(idx->ntotal_mutex);
+    idx->ntotal += n;
+  }
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  if (seconds_out) *seconds_out = secs;
+  if (gbytes_out) *gbytes_out = static_cast<double>(n) * (kD * 4 + 8) / 1e9;
+  return B2F_OK;
+}
+
+extern "C" int b2f_rank_dedup_device(b2f_index* idx, const int64_t* I_dev, const float* D32_dev, const double* D64_dev,
+                                     int64_t nq, int64_t in_stride, int topN, const int64_t* offset2pid_dev,
+                                     int64_t n_offsets, int64_t* pid_out_dev, double* score_out_dev, int* count_out_dev) {
+  if (!idx || nq < 0 || topN < 1 || topN > B2F_MAX_K || in_stride < topN || !I_dev || (!D32_dev && !D64_dev) ||
+      !offset2pid_dev || n_offsets < 1 || !pid_out_dev || !score_out_dev || !count_out_dev)
+    return fail(B2F_ERR_INVALID, "bad rank_dedup arguments");
+  if (nq == 0) return B2F_OK;
+  Shard& S = idx->shards[0];
+  CU_TRY(cudaSetDevice(S.dev));
+  rank_dedup_kernel<<<static_cast<int>(nq), kDedupThreads, static_cast<size_t>(topN) * 12, S.stream>>>(
+      I_dev, D32_dev, D64_dev, in_stride, topN, offset2pid_dev, n_offsets, pid_out_dev, score_out_dev, count_out_dev);
+  CU_TRY(cudaGetLastError());
+  idx->stats.launches += 1;
+  CU_TRY(cudaStreamSynchronize(S.stream));
+  return B2F_OK;
+}

@@ -820,4 +820,70 @@ __global__ void __launch_bounds__(256) xchg_merge_kernel(const char* __restrict_
              D, I, part_cap / 4, part_cap / 8, saw_overflow, &total_valid, staged, merge_smem);
 }
 
+// ---------------------------------------------------------------------------------------------
+// EvalDevQuery's id handling on device (reference drivers/run_convdr_inference.py:43-69): for every query,
+// the first topN entries of the merged ranking (passage offsets, best first) are translated with
+// pid = offset2pid[offset]; a pid that already appeared at a better rank is dropped; the survivors keep their
+// order and move to the front; unfilled tail slots hold (pid 0, score 0) exactly like the reference's
+// pre-filled `[(0, 0)] * topN`.  A negative offset indexes from the end (Python semantics: the reference's
+// `-1` wrap of a short block, :190).  One block per query; the pids of the row live in shared memory and
+// position i looks for an equal pid among positions < i.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDedupThreads = 256;
+__global__ void __launch_bounds__(kDedupThreads) rank_dedup_kernel(
+    const int64_t* __restrict__ I, const float* __restrict__ D32, const double* __restrict__ D64, int64_t in_stride,
+    int topN, const int64_t* __restrict__ offset2pid, int64_t n_offsets, int64_t* __restrict__ pid_out,
+    double* __restrict__ score_out, int* __restrict__ count_out) {
+  extern __shared__ __align__(16) unsigned char dd_smem[];
+  int64_t* pid_s = reinterpret_cast<int64_t*>(dd_smem);                        // [topN]
+  int* keep_s = reinterpret_cast<int*>(dd_smem + sizeof(int64_t) * topN);      // [topN] then exclusive ranks
+  __shared__ int warp_tot[kDedupThreads / 32];
+  __shared__ int running;
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < topN; i += kDedupThreads) {
+    int64_t off = I[q * in_stride + i];
+    if (off < 0) off += n_offsets;
+    pid_s[i] = (off >= 0 && off < n_offsets) ? offset2pid[off] : -1;           // out of range: never equal to a real pid
+  }
+  if (tid == 0) running = 0;
+  __syncthreads();
+  for (int i = tid; i < topN; i += kDedupThreads) {
+    const int64_t p = pid_s[i];
+    int first = 1;
+    for (int j = 0; j < i; ++j) first &= (pid_s[j] != p);
+    keep_s[i] = first;
+  }
+  __syncthreads();
+  // compaction: ranks in position order, chunk by chunk
+  for (int i0 = 0; i0 < topN; i0 += kDedupThreads) {
+    const int i = i0 + tid;
+    const int kp = (i < topN) ? keep_s[i] : 0;
+    int v = kp;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, sft);
+      if (lane >= sft) v += t;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    int base = running;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    if (kp) {
+      const int r = base + v - 1;
+      pid_out[q * topN + r] = pid_s[i];
+      score_out[q * topN + r] = D64 ? D64[q * in_stride + i] : static_cast<double>(D32[q * in_stride + i]);
+    }
+    __syncthreads();
+    if (tid == kDedupThreads - 1) running = base + v;
+    __syncthreads();
+  }
+  const int n_kept = running;
+  for (int i = n_kept + tid; i < topN; i += kDedupThreads) {
+    pid_out[q * topN + i] = 0;
+    score_out[q * topN + i] = 0.0;
+  }
+  if (tid == 0) count_out[q] = n_kept;
+}
+
 }  // namespace b2f

@@ -297,7 +297,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
         if (streamed && ++sq == static_cast<uint32_t>(a.q_stages)) { sq = 0; pq ^= 1u; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + kQsEpiWarps) {
     // ===================== epilogue: filter + append =====================
     const int ew = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 4) >> 2;        // which of the alternating 16-query chunks

@@ -120,6 +120,37 @@ class FlatIPIndex:
     def reserve(self, n_per_shard: int) -> None:
         _lib.check(_lib.load().b2f_reserve(self._ensure(), int(n_per_shard)))
 
+    def add_flat_file(self, path: str, shard: int = 0, threads: int = 4):
+        """Stream one flat shard file (blocks.py format) into shard `shard` through pinned staging buffers
+        (b2f_add_flat_file); the stored passage offsets become the labels.  Returns (seconds, gigabytes).
+        Thread-safe across different shards: ctypes releases the GIL, one host thread per GPU keeps every
+        PCIe link busy."""
+        secs, gb = C.c_double(), C.c_double()
+        _lib.check(_lib.load().b2f_add_flat_file(self._ensure(), int(shard), str(path).encode(), int(threads),
+                                                 C.byref(secs), C.byref(gb)))
+        return float(secs.value), float(gb.value)
+
+    def rank_dedup(self, I, D, topN: int, offset2pid):
+        """EvalDevQuery's id handling on device (reference drivers/run_convdr_inference.py:43-69): I [nq, >=topN]
+        int64 offsets (best first), D float32/float64 scores, offset2pid int64 [n] — all CUDA tensors on the
+        index's device.  Returns (pids int64 [nq, topN], scores float64 [nq, topN], counts int32 [nq]): the
+        first topN entries translated to pids with repeated pids dropped, survivors first, tail (0, 0.0)."""
+        import torch
+        assert I.is_cuda and D.is_cuda and offset2pid.is_cuda and I.dtype == torch.int64 and offset2pid.dtype == torch.int64
+        assert I.dim() == 2 and D.shape == I.shape and I.shape[1] >= topN and I.stride(1) == 1 and D.stride(1) == 1
+        assert D.dtype in (torch.float32, torch.float64) and I.stride(0) == D.stride(0)
+        nq = I.shape[0]
+        pid = torch.empty((nq, topN), dtype=torch.int64, device=I.device)
+        sc = torch.empty((nq, topN), dtype=torch.float64, device=I.device)
+        cnt = torch.empty((nq,), dtype=torch.int32, device=I.device)
+        d32 = D.data_ptr() if D.dtype == torch.float32 else None
+        d64 = D.data_ptr() if D.dtype == torch.float64 else None
+        torch.cuda.current_stream(I.device).synchronize()
+        _lib.check(_lib.load().b2f_rank_dedup_device(self._ensure(), I.data_ptr(), d32, d64, nq, I.stride(0), int(topN),
+                                                     offset2pid.data_ptr(), offset2pid.numel(), pid.data_ptr(),
+                                                     sc.data_ptr(), cnt.data_ptr()))
+        return pid, sc, cnt
+
     def add_device(self, x, shard: int = 0) -> None:
         """Append a CUDA float32 torch tensor [n, d] living on the shard's device (no host copy)."""
         assert x.is_cuda and x.dtype.is_floating_point and x.dim() == 2 and x.shape[1] == self.d

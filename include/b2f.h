@@ -73,6 +73,17 @@ int b2f_add_with_ids(b2f_index* idx, const float* x_host, const int64_t* ids_hos
 /* Zero-copy variant: x_dev is device memory on shard `shard`'s device.         */
 int b2f_add_device(b2f_index* idx, int shard, const float* x_dev, int64_t n);
 
+/* Resident load ("search all at once", reference README.md:216; replaces the
+ * per-run `pickle.load` + `index.add` of reference :161-180): stream ONE flat
+ * shard file (convdr_b200/blocks.py: 64-byte header, float32 rows, int64 passage
+ * offsets) into shard `shard`.  n_threads reader threads pread() 24 MB pieces into
+ * pinned staging buffers while earlier pieces cross PCIe; the stored offsets become
+ * the labels search returns (like b2f_add_with_ids).  Calls for DIFFERENT shards may
+ * run concurrently from different host threads.  seconds_out / gbytes_out (may be
+ * NULL) report the wall time and the bytes moved.                                 */
+int b2f_add_flat_file(b2f_index* idx, int shard, const char* path, int n_threads,
+                      double* seconds_out, double* gbytes_out);
+
 /* Pre-size every shard for `n_per_shard` rows (avoids regrowth copies).        */
 int b2f_reserve(b2f_index* idx, int64_t n_per_shard);
 
@@ -129,6 +140,19 @@ int b2f_merge_packed_device_async(b2f_index* idx, const void* parts_dev, int n_p
                                   int64_t part_bytes, int64_t i_offset_bytes, int64_t nq, int k,
                                   float* D_dev, int64_t* I_dev);
 
+/* EvalDevQuery's ranking clean-up on device (reference :43-69): for each of the nq
+ * rows of I_dev (passage offsets, best first; row stride in_stride >= topN) take the
+ * first topN entries, translate pid = offset2pid[offset] (a negative offset indexes
+ * from the end, like the Python list it replaces), drop every pid that already
+ * appeared at a better rank, compact the survivors to the front (pid_out, score_out:
+ * [nq, topN]; the tail is filled with pid 0 / score 0 like the reference's
+ * `[(0, 0)] * topN`) and report how many survived (count_out [nq]).  Scores come
+ * from D32_dev (float32) or D64_dev (float64), whichever is non-NULL.              */
+int b2f_rank_dedup_device(b2f_index* idx, const int64_t* I_dev, const float* D32_dev,
+                          const double* D64_dev, int64_t nq, int64_t in_stride, int topN,
+                          const int64_t* offset2pid_dev, int64_t n_offsets,
+                          int64_t* pid_out_dev, double* score_out_dev, int* count_out_dev);
+
 /* Peer-memory exchange for the one-process-per-GPU layout (one single-shard index
  * per rank, all ranks on one NVLink/NVSwitch node): replaces ncclAllGather +
  * merge by two kernels that talk through CUDA-IPC-mapped buffers.
@@ -174,25 +198,35 @@ int b2f_num_shards(const b2f_index* idx);
 void* b2f_stream(b2f_index* idx, int shard);
 
 /* Tuning knobs:
- *   "path" (B2F_PATH_*), "shadow" (keep the bf16 copy, default 1), "keep_on_reset" (default 1),
- *   "scan_max_auto" (largest batch AUTO sends to the SIMT scan, default 4),
+ *   "path" (B2F_PATH_*; AUTO = the tensor engine whenever the bf16 shadow exists),
+ *   "shadow" (keep the bf16 copy, default 1), "keep_on_reset" (default 1),
+ *   "scan_max_auto" (largest batch AUTO sends to the SIMT scan, default 0 = never),
+ *   "center" (default 1: the shadow holds rows minus the mean of the first rows added, so the error
+ *       margin follows ||p - mean|| instead of ||p||; empty index only),
  *   "margin_ppm" (scale of the rigorous error margin in parts-per-million, default 1000000),
  *   "worst_case_margin" (1: data-independent 2^-8 bound instead of the per-shard rounding-error
  *       bound; A/B only),
- *   "umma_variant" (tensor engine: 0 auto, 1 SS = queries in shared memory, 2 TS = queries in TMEM),
+ *   "umma_variant" (tensor engine: 0 auto = QS for passes of up to "qs_max_q" (208) queries, TS above;
+ *       2 TS = queries in TMEM, MMA M = 256 query lanes; 3 QS = queries on the MMA N side; 1 = QS with
+ *       every query K-block resident in shared memory), "qs_resident_kb" (QS: resident query K-blocks,
+ *       default 12; the rest is streamed from L2 through a ring of "qs_q_stages" stages),
+ *   "synth_mean_shift" (b2f_add_synthetic: integer shift M of every component along a fixed sign
+ *       vector per seed, 0 = isotropic rows; see convdr_b200/synth.py),
  *   "tighten" (TS engine: in-kernel threshold tightening, minimum pause of the refresher warp in
  *       ns, default 2000; 0 = geometric phases with a refresh kernel between them),
  *   "tighten_adaptive" (default 1: the pause grows with the elapsed kernel time),
  *   "bootstrap" (default 0: thresholds start at -inf inside the single launch; 1: dense bootstrap
  *       launch + bootstrap_select_kernel first), "growth" (phase growth factor of the phased
- *       schedules), "l2_prefetch" (SS variant: prefetch distance in tiles),
+ *       schedules),
  *   "profile" (1: CUDA events around every scoring / selection launch),
  *   "reset_stats" (any value: zero the counters below).                          */
 int b2f_set_option(b2f_index* idx, const char* key, int64_t value);
 
 /* Counters since the last synchronous search started (asynchronous searches
  * accumulate): "launches", "phases", "candidates",
- * "fallback_queries", "path", "passes"; with "profile" on also "score_ms",
+ * "fallback_queries" (queries re-run on the exact engine) and why: "overflow_area" (a private list
+ * area was too small), "overflow_survivors" (more rows within the error margin of the k-th score
+ * than the survivor buffer holds); "path", "passes", "qs_passes"; with "profile" on also "score_ms",
  * "score_launches", "score_rows" (scoring kernels: device time, launches, rows
  * streamed) and "select_ms" (refresh + final kernels).                         */
 int b2f_get_stat(const b2f_index* idx, const char* key, double* out);

@@ -214,6 +214,32 @@ def search_one_by_one(ann_data_dir: str, index, query_embedding: np.ndarray, top
     return run_s, run_i
 
 
+def eval_rank_dedup(merged_D, merged_I, topN: int, offset2pid):
+    """What `EvalDevQuery` does with the merged ranking before anything is written (reference
+    drivers/run_convdr_inference.py:37-69): per query, the first topN (offset, score) pairs in rank order,
+    `pred_pid = offset2pid[idx]` (:62; a negative idx wraps like any Python sequence index), a pid already in
+    `seen_pid` is skipped (:64), the others take ranks 0, 1, ... (:65-71); slots never reached keep the
+    pre-filled `(0, 0)` (:50).  Returns (pids int64 [nq, topN], scores float64 [nq, topN], counts int32 [nq])."""
+    nq = len(merged_I)
+    pids = np.zeros((nq, topN), dtype=np.int64)
+    scores = np.zeros((nq, topN), dtype=np.float64)
+    counts = np.zeros((nq,), dtype=np.int32)
+    for query_idx in range(nq):
+        seen_pid = set()
+        rank = 0
+        selected_ann_idx = merged_I[query_idx][:topN]
+        selected_ann_score = np.asarray(merged_D[query_idx][:topN]).tolist()
+        for idx, score in zip(selected_ann_idx, selected_ann_score):
+            pred_pid = int(offset2pid[int(idx)])
+            if pred_pid not in seen_pid:
+                pids[query_idx, rank] = pred_pid
+                scores[query_idx, rank] = score
+                rank += 1
+                seen_pid.add(pred_pid)
+        counts[query_idx] = rank
+    return pids, scores, counts
+
+
 # ---------------------------------------------------------------------------------------------
 # Ground truth and comparator
 # ---------------------------------------------------------------------------------------------

@@ -185,3 +185,14 @@ def test_synth_host_twins_agree_bit_for_bit():
     z = np.zeros(1, dtype=np.uint64)
     kat = [int(x[0]) for x in synth.philox4x32_10(z, z, z, z, 0, 0)]
     assert kat == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]  # Random123 known-answer vector
+
+
+def test_eval_rank_dedup_keeps_first_occurrences_in_rank_order():
+    # reference drivers/run_convdr_inference.py:37-69: two offsets of one passage -> the better rank stays
+    offset2pid = np.array([10, 11, 10, 12, 13, 11], dtype=np.int64)
+    I = np.array([[0, 2, 1, 5, 3, 4], [4, 3, -1, 5, 0, 2]], dtype=np.int64)
+    D = np.array([[.9, .8, .7, .6, .5, .4], [.9, .8, .7, .6, .5, .4]])
+    pids, scores, counts = flat_ip.eval_rank_dedup(D, I, 5, offset2pid)
+    assert pids[0].tolist() == [10, 11, 12, 0, 0] and counts[0] == 3          # only the first 5 entries are read
+    assert scores[0].tolist() == [.9, .7, .5, 0.0, 0.0]
+    assert pids[1].tolist() == [13, 12, 11, 10, 0] and counts[1] == 4         # -1 wraps to the last offset (pid 11)

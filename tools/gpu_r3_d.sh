@@ -2,10 +2,10 @@
 # round 2, call D: first-tile protocol + refresher priority: tests, fallback counts, batch-size/variant sweep
 mkdir -p gpurun_out
 echo "=== gpu tests"
-timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/r3d_tests.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/r3d_tests.log
+timeout 400 python -m pytest tests -q -m gpu -x --timeout 120 > gpurun_out/r3d_tests.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/r3d_tests.log
 run() { # tag, args...
   tag=$1; shift
-  timeout 900 python bench.py --no-cpu-baseline --no-oracle-check "$@" > gpurun_out/r3d_$tag.json 2> gpurun_out/r3d_$tag.err; rc=$?
+  timeout 150 python bench.py --no-cpu-baseline --no-oracle-check "$@" > gpurun_out/r3d_$tag.json 2> gpurun_out/r3d_$tag.err; rc=$?
   python - <<PY
 import json
 try:
