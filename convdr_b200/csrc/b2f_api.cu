@@ -294,7 +294,7 @@ struct b2f_index {
   int qs_q_stages = 3;    // QS: depth of the query ring
   int center = 1;         // subtract the collection mean (first rows of the first add) before the bf16 rounding
   int synth_mean_shift = 0;  // b2f_add_synthetic: integer shift of every component along a fixed sign vector
-  int l2_prefetch = 1;
+  int l2_prefetch = 1;    // QS: L2 prefetch distance of the passage producer, in tiles (0 = off)
   int worst_case_margin = 0;  // 1: bf16 margin from the data-independent worst case (A/B only)
   int tighten_adaptive = 1;  // refresher pause grows with the elapsed kernel time (see UmmaArgs)
   int bootstrap = 0;      // TS engine with tightening: 1 = dense bootstrap launch + bootstrap_select_kernel before the
@@ -692,6 +692,9 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     // histogram: 2 * pairs * 32 rows per quarter, about half of which score above the histogram floor), the
     // other quarters wait until every query has a threshold (bounded: first_wait_cycles).  Shards too small
     // to fill the first tiles do not wait.
+    a.x16_bytes = reinterpret_cast<const unsigned char*>(S.x16);
+    a.pf_limit_bytes = shadow_rows_padded(N) * static_cast<int64_t>(kD) * 2;
+    a.prefetch = idx->l2_prefetch;
     a.dense_quarters = std::min(4, std::max(1, (4 * k + 2 * pairs * 32 - 1) / (2 * pairs * 32)));
     a.first_wait_cycles = (idx->tighten && N >= 4ll * pairs * kQsTileRows && a.dense_quarters < 4) ? 100000 : 0;
     {
