@@ -1,4 +1,4 @@
-"""In-tree build of the CUDA library (sm_100a only) and of the oracle's C restatement.
+"""In-tree build of the CUDA library (sm_100a only).
 
 `python -m convdr_b200.build` or `__graft_entry__.build()`.  nvcc cross-compiles without a GPU.
 The built `.so` files are git-ignored but travel with the repo snapshot to the GPU box.
@@ -48,19 +48,9 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_oracle(force: bool = False) -> None:
-    """Compile oracle/'s C restatement (test infrastructure; never loaded by the product path)."""
-    odir = os.path.join(ROOT, "oracle")
-    if os.path.exists(os.path.join(odir, "Makefile")):
-        res = subprocess.run(["make", "-C", odir] + (["-B"] if force else []), capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
-
-
 def main() -> None:
     force = "--force" in sys.argv
     print(build_cuda(force=force, verbose="-v" in sys.argv))
-    build_oracle(force=force)
 
 
 if __name__ == "__main__":

@@ -102,6 +102,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint32_t c
 }
 
 constexpr int kMaxPending = 16;
+constexpr int kLoadBufs = 6;            // pinned staging buffers of the flat-file loader
+constexpr int64_t kLoadPieceRows = 8192; // rows per staged piece (24 MB)
 constexpr int kMuBlocks = 256;          // partial column sums of the centre
 constexpr int64_t kMuRows = 65536;      // the centre is the mean of (up to) the first 65536 rows of the first add   // asynchronous device searches in flight (one overflow-flag slot each)
 
@@ -182,6 +184,8 @@ struct Shard {
   float* mu = nullptr;               // device [768]: the shard's centre (zeros until set / when centring is off)
   float* mu_part = nullptr;          // device [kMuBlocks][768]: partial column sums
   bool mu_set = false;
+  char* load_bufs[kLoadBufs] = {nullptr};       // pinned staging ring of b2f_add_flat_file (allocated on first use)
+  cudaEvent_t load_evs[kLoadBufs] = {nullptr};
   int64_t* idmap = nullptr;          // optional explicit labels [cap]
   bool has_ids = false;
   std::vector<Seg> segs;
@@ -294,7 +298,7 @@ struct b2f_index {
   int qs_q_stages = 3;    // QS: depth of the query ring
   int center = 1;         // subtract the collection mean (first rows of the first add) before the bf16 rounding
   int synth_mean_shift = 0;  // b2f_add_synthetic: integer shift of every component along a fixed sign vector
-  int l2_prefetch = 1;    // QS: L2 prefetch distance of the passage producer, in tiles (0 = off)
+  int l2_prefetch = 0;    // QS: distance (tiles) of the optional L2 prefetch warp; 0 = off (default: measured slower)
   int worst_case_margin = 0;  // 1: bf16 margin from the data-independent worst case (A/B only)
   int tighten_adaptive = 1;  // refresher pause grows with the elapsed kernel time (see UmmaArgs)
   int bootstrap = 0;      // TS engine with tightening: 1 = dense bootstrap launch + bootstrap_select_kernel before the
@@ -621,7 +625,7 @@ PassPlan make_plan(const b2f_index* idx, const Shard& S, int path, int k, int64_
     // expected appends per (query, area) in a phase: 2 (margin) * (growth-1) * k / areas; x2 safety
     // (with in-kernel tightening the pass rate follows k/rows_seen, far fewer appends; keep the bound)
     const int64_t expect = 4ll * (std::max(2, idx->growth) - 1) * k / S.max_pairs;
-    p.cap_p = static_cast<int>(round_up(std::max<int64_t>(std::max<int64_t>(512, t0 * kTileRows), expect), 32));
+    p.cap_p = static_cast<int>(round_up(std::max<int64_t>(std::max<int64_t>(512, t0 * kTileRows), expect), 64));   // per pair; half per (pair, half tile)
     p.cap_a = static_cast<int>(round_up(std::max<int64_t>(512, kQsTileRowsCta + expect / 2), 32));
     p.C = p.S + std::max(S.max_pairs * p.cap_p, 2 * S.max_pairs * p.cap_a);
   } else {
@@ -664,7 +668,8 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   } else {
     W.areas_clean = false;  // flat lists / one-launch passes leave records behind in the areas
   }
-  const int n_areas = tensor_qs ? 2 * S.max_pairs : S.max_pairs;
+  const int n_areas = 2 * S.max_pairs;   // TS: two per CTA pair (one per half tile); QS: one per CTA
+  const int cap_h = plan.cap_p / 2;       // TS: slots per (query, pair, half tile)
   const int margin_mode = plan.exact ? 0 : (plan.path == B2F_PATH_UMMA_BF16 ? (idx->worst_case_margin ? 3 : 2) : 1);
   pass_init_kernel<<<nqp, 128, 0, s>>>(qnormp, qerrp, S.maxnorm2, margin_mode,
                                        static_cast<float>(idx->margin_ppm * 1e-6 * 1.0000001), static_cast<float>(kUScan),
@@ -748,8 +753,8 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       if (end < N) end = static_cast<int64_t>(te) * kTileRows;  // phases end on tile boundaries
       UmmaArgs a;
       a.n_rows = N; a.tile_begin = tb; a.tile_end = te; a.nq = nqp; a.q16 = q16p;
-      a.dense = dense ? 1 : 0; a.cand = W.cand[cur]; a.C = C; a.S = plan.S; a.cap_p = plan.cap_p;
-      a.max_pairs = S.max_pairs; a.cnt2 = W.cnt2; a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
+      a.dense = dense ? 1 : 0; a.cand = W.cand[cur]; a.C = C; a.S = plan.S; a.cap_p = cap_h;
+      a.max_pairs = n_areas; a.cnt2 = W.cnt2; a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
       a.tighten = idx->tighten; a.tighten_adaptive = idx->tighten_adaptive; a.k = k; a.margin = W.margin; a.hist = W.hist; a.hkey0 = W.hkey0; a.hshift = W.hshift;
       const int pairs = std::min(S.max_pairs, te - tb);
       {
@@ -786,13 +791,13 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       int P = 4096;
       while (P < plan.n0 + plan.S && P < 16384) P <<= 1;   // longer lists are gathered to global memory
       bootstrap_select_kernel<<<nqp, kFinThreads, static_cast<size_t>(P) * sizeof(uint64_t), s>>>(
-          W.cand[cur], W.cand[cur ^ 1], W.gath, W.cnt, C, k, W.margin, W.tau, plan.S, plan.cap_p, S.max_pairs, W.cnt2,
+          W.cand[cur], W.cand[cur ^ 1], W.gath, W.cnt, C, k, W.margin, W.tau, plan.S, cap_h, n_areas, W.cnt2,
           W.ovf, W.hist, W.hkey0, W.hshift, P);
     } else {
       ProfScope ps(idx, S, 1);
       refresh_kernel<<<nqp, kSelThreads, 0, s>>>(W.cand[cur], W.cand[cur ^ 1], W.gath, W.cnt, C, k, plan.exact ? 1 : 0,
-                                                W.margin, W.tau, W.tauP, n_override, plan.S, plan.cap_p,
-                                                tensor ? S.max_pairs : 0, W.cnt2, W.ovf,
+                                                W.margin, W.tau, W.tauP, n_override, plan.S, cap_h,
+                                                tensor ? n_areas : 0, W.cnt2, W.ovf,
                                                 (tensor && idx->tighten && end < N) ? W.hist : nullptr, W.hkey0, W.hshift);
     }
     CU_TRY(cudaGetLastError());
@@ -809,7 +814,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     int P = 8192;                        // gathered list (bufA); longer lists go through global memory
     while (P < PS) P <<= 1;
     finalize_kernel<<<nqp, kFinThreads, static_cast<size_t>(P + PS) * sizeof(uint64_t), s>>>(
-        W.cand[cur], W.gath, W.cnt, C, k, W.margin, plan.S, plan.cap_p, S.max_pairs, W.cnt2, W.ovf, ovf_dst, q32p,
+        W.cand[cur], W.gath, W.cnt, C, k, W.margin, plan.S, cap_h, n_areas, W.cnt2, W.ovf, ovf_dst, q32p,
         S.x32, S.segs_d, static_cast<int>(S.segs.size()), S.has_ids ? S.idmap : nullptr, D_out, I_out, out_stride, P,
         idx->tighten ? W.tau : nullptr);
     CU_TRY(cudaGetLastError());
@@ -1100,6 +1105,10 @@ void b2f_destroy(b2f_index* idx) {
     Workspace& W = S.ws;
     dev_free(S.x32); dev_free(S.x16); dev_free(S.idmap); dev_free(S.maxnorm2); dev_free(S.segs_d);
     dev_free(S.mu); dev_free(S.mu_part);
+    for (int b = 0; b < kLoadBufs; ++b) {
+      if (S.load_bufs[b]) cudaFreeHost(S.load_bufs[b]);
+      if (S.load_evs[b]) cudaEventDestroy(S.load_evs[b]);
+    }
     dev_free(W.cand[0]); dev_free(W.cand[1]); dev_free(W.cnt); dev_free(W.tau); dev_free(W.tauP);
     dev_free(W.ovf); dev_free(W.margin); dev_free(W.err); dev_free(W.q32); dev_free(W.q16);
     dev_free(W.gath); dev_free(W.cnt2); dev_free(W.hist); dev_free(W.hkey0); dev_free(W.hshift);
@@ -1719,17 +1728,21 @@ extern "C" int b2f_add_flat_file(b2f_index* idx, int shard, const char* path, in
   B2F_TRY(ensure_capacity(idx, S, S.n + n));
   const auto t_begin = std::chrono::steady_clock::now();
 
-  constexpr int64_t kPieceRows = 8192;                     // 24 MB per piece
-  constexpr int kBufs = 6;
+  constexpr int64_t kPieceRows = kLoadPieceRows;
+  constexpr int kBufs = kLoadBufs;
   const size_t piece_bytes = static_cast<size_t>(kPieceRows) * kD * 4;
   const int64_t n_pieces = (n + kPieceRows - 1) / kPieceRows;
-  const int T = std::max(1, std::min(n_threads > 0 ? n_threads : 4, 16));
-  char* bufs[kBufs] = {nullptr};
-  cudaEvent_t evs[kBufs] = {nullptr};
+  // reader threads: a pread from the page cache is a ~3 GB/s memcpy, a PCIe 5 x16 link takes ~50 GB/s: by
+  // default the host's cores are shared out over the shards (each shard is loaded by its own caller thread)
+  const int hw = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+  const int T = n_threads > 0 ? std::min(n_threads, 32)
+                              : std::max(2, std::min(12, hw / static_cast<int>(idx->shards.size())));
+  char** bufs = S.load_bufs;
+  cudaEvent_t* evs = S.load_evs;
   int rc = B2F_OK;
-  for (int b = 0; b < kBufs && rc == B2F_OK; ++b) {
-    if (cudaMallocHost(reinterpret_cast<void**>(&bufs[b]), piece_bytes) != cudaSuccess ||
-        cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming) != cudaSuccess) {
+  for (int b = 0; b < kBufs && rc == B2F_OK; ++b) {   // pinned allocations are slow (~100 ms): kept for the next file
+    if ((!bufs[b] && cudaMallocHost(reinterpret_cast<void**>(&bufs[b]), piece_bytes) != cudaSuccess) ||
+        (!evs[b] && cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming) != cudaSuccess)) {
       (void)cudaGetLastError();
       rc = fail(B2F_ERR_OOM, "pinned staging allocation failed");
     }
@@ -1796,10 +1809,6 @@ extern "C" int b2f_add_flat_file(b2f_index* idx, int shard, const char* path, in
     for (std::thread& th : readers) th.join();
     if (failed.load() == 1) rc = fail(B2F_ERR_INVALID, std::string(path) + ": read error");
     else if (failed.load() == 2) { (void)cudaGetLastError(); rc = fail(B2F_ERR_CUDA, "copy of a staged piece failed"); }
-  }
-  for (int b = 0; b < kBufs; ++b) {
-    if (bufs[b]) cudaFreeHost(bufs[b]);
-    if (evs[b]) cudaEventDestroy(evs[b]);
   }
   if (rc != B2F_OK) return rc;
   B2F_TRY(ingest_rows(idx, S, n));

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kSelThreads) refresh_kernel(
     int* __restrict__ cnt2, int* __restrict__ ovf, unsigned int* __restrict__ hist /* [nq][kTightenBuckets] or null */,
     uint32_t* __restrict__ hkey0, int* __restrict__ hshift) {
   __shared__ SelectSmem sm;
-  __shared__ int seg_off[128];
+  __shared__ int seg_off[256];
   const int q = blockIdx.x;
   const uint64_t* in = cand_in + static_cast<int64_t>(q) * C;
   uint64_t* out = cand_out + static_cast<int64_t>(q) * C;

@@ -24,7 +24,8 @@
 
 namespace b2f {
 
-constexpr int kUmmaThreads = 256;
+constexpr int kUmmaThreads = 384;                // 4 service warps + 8 epilogue warps (two per TMEM lane quarter)
+constexpr int kUmmaEpiWarps = 8;
 constexpr int kBlockK = 64;                    // bf16 per K-block = 128 bytes (one swizzle span)
 constexpr int kNumKBlocks = kD / kBlockK;      // 12
 constexpr int kTileRowsCta = kShadowTileRows;  // passage rows per CTA per tile (32)
@@ -56,10 +57,11 @@ struct UmmaArgs {
   int dense;                  // 1: store every score (bootstrap phase), 0: threshold filter
   // Candidate list of query q: cand[q*C .. q*C+C).  [0, S) holds the survivors of earlier phases
   // (written by refresh_kernel); the rest is split in `max_pairs` private areas of `cap_p` slots,
-  // one per CTA pair, so the thread that owns (query, pair) appends without any atomic.
+  // TWO per CTA pair (one per half of a tile's 64 rows), so the thread that owns (query, pair, half)
+  // appends without any atomic.
   uint64_t* cand;
-  int C, S, cap_p, max_pairs;
-  int* cnt2;                  // [nq][max_pairs] entries written by each pair in this launch
+  int C, S, cap_p, max_pairs; // max_pairs = number of areas = 2 x CTA pairs of the largest grid
+  int* cnt2;                  // [nq][max_pairs] entries written to each area in this launch
   float* tau;                 // [nq] thresholds (raised in-kernel when tighten != 0)
   int* ovf;                   // [nq] set when a private area was too small
   int* err;                   // device error flag (barrier timeout)
@@ -301,12 +303,16 @@ __device__ __forceinline__ bool any_ge32(const uint32_t* v, float tau) {
 }
 
 // ------------------------------------------------------------------------------------------
-// The kernel.  Grid = 2 * (number of CTA pairs), cluster (2,1,1), 256 threads:
-//   warp 0 lane 0 : TMA producer (both CTAs stream their own 64 rows of every tile)
+// The kernel.  Grid = 2 * (number of CTA pairs), cluster (2,1,1), 384 threads:
+//   warp 0 lane 0 : TMA producer (both CTAs stream their own 32 rows of every tile)
 //   warp 1 lane 0 : MMA issuer (leader CTA only)
 //   warp 2        : TMEM allocation / release
-//   warps 4..7    : load the queries into TMEM, then epilogue — thread (rank, lane) owns query
-//                   128*rank + 32*(warp%4) + lane
+//   warp 3        : refresher (in-kernel threshold tightening)
+//   warps 4..11   : load the queries into TMEM, then epilogue — thread (rank, lane) of warp w owns query
+//                   128*rank + 32*(w%4) + lane and, of every 64-row tile, the 32 rows of half (w-4)/4: two
+//                   threads per query, each with its own private list area (hit handling is per-thread
+//                   instruction overhead in a warp that the scheduler cannot hide: two warps per TMEM lane
+//                   quarter halve it and overlap each other's latencies)
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     umma_score_select_kernel(const __grid_constant__ CUtensorMap tmap_p, const UmmaArgs a) {
@@ -337,10 +343,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
       mbar_init(bar_full + 8 * s, 2);   // leader's expect_tx arrive + peer's remote arrive
       mbar_init(bar_empty + 8 * s, 1);  // one multicast commit
     }
-    mbar_init(bar_qready, 8);           // 4 query-loading warps x 2 CTAs
+    mbar_init(bar_qready, 2 * kUmmaEpiWarps);           // query-loading warps x 2 CTAs
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);   // one multicast commit
-      mbar_init(bar_tempty + 8 * s, 8);  // 4 epilogue warps x 2 CTAs (leader's copy is the one used)
+      mbar_init(bar_tempty + 8 * s, 2 * kUmmaEpiWarps);  // epilogue warps x 2 CTAs (leader's copy is the one used)
     }
     fence_mbar_init();
   }
@@ -408,6 +414,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
   } else if (warp >= 4) {
     // ===================== queries -> TMEM, then epilogue =====================
     const int ew = warp & 3;
+    const int half = (warp - 4) >> 2;      // which 32 rows of every 64-row tile / which half of the query columns to load
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     const int q = static_cast<int>(cta_rank) * 128 + ew * 32 + lane;
     const bool q_ok = q < a.nq;
@@ -418,7 +425,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
       constexpr int kQChunk = 3;
       static_assert((kTmemColsA / 32) % kQChunk == 0, "query row = whole rounds");
 #pragma unroll 1
-      for (int c0 = 0; c0 < kTmemColsA / 32; c0 += kQChunk) {   // 32 columns = 64 bf16 = 128 bytes per chunk
+      static_assert((kTmemColsA / 64) % kQChunk == 0, "each of the two warps of a quarter loads whole rounds");
+      for (int c0 = half * (kTmemColsA / 64); c0 < (half + 1) * (kTmemColsA / 64); c0 += kQChunk) {   // 32 columns = 64 bf16 = 128 bytes per chunk
         uint32_t w[kQChunk][32];
 #pragma unroll
         for (int u = 0; u < kQChunk; ++u)
@@ -437,12 +445,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     }
     float tau = (q_ok && !a.dense) ? a.tau[q] : INFINITY;
     volatile float* tau_g = a.tau + (q_ok ? q : 0);
-    int* my_cnt = a.cnt2 + (q_ok ? q : 0) * a.max_pairs + pair;
+    const int area = 2 * pair + half;
+    int* my_cnt = a.cnt2 + (q_ok ? q : 0) * a.max_pairs + area;
     const bool live = a.tighten && q_ok && !a.dense;
     const uint32_t hkey0 = live ? a.hkey0[q] : 0xffffffffu;
     const int hshift = live ? a.hshift[q] : 0;
     unsigned int* my_hist = a.hist + static_cast<int64_t>(q_ok ? q : 0) * kHistStride;
-    uint64_t* my_list = a.cand + static_cast<int64_t>(q_ok ? q : 0) * a.C + a.S + static_cast<int64_t>(pair) * a.cap_p;
+    uint64_t* my_list = a.cand + static_cast<int64_t>(q_ok ? q : 0) * a.C + a.S + static_cast<int64_t>(area) * a.cap_p;
     int n_mine = 0;   // entries this thread appended for (query q, this pair)
     // count a hit in the tightening histogram (fire-and-forget RED; hits are rare)
     auto count_hit = [&](uint32_t bits) {
@@ -462,64 +471,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
       mbar_wait(bar_tfull + 8 * as, aph, a.err);
       tc_fence_after();
       tau = fmaxf(tau, tau_new);             // thresholds only rise
-      uint32_t v[kTileRows];
-#pragma unroll
-      for (int w = 0; w < kTileRows / 32; ++w) tmem_ld_x32(lane_addr + kTmemColD + as * kTileRows + 32 * w, v + 32 * w);
+      constexpr int kHalfRows = kTileRows / 2;   // 32: this thread's rows of the tile
+      uint32_t v[kHalfRows];
+      const uint32_t col0 = lane_addr + kTmemColD + as * kTileRows + kHalfRows * half;
+      tmem_ld_x32(col0, v);
       tmem_ld_wait();
-      const int64_t row0 = static_cast<int64_t>(tile) * kTileRows;
-      const int n_valid = static_cast<int>(min(static_cast<int64_t>(kTileRows), a.n_rows - row0));
+      const int64_t row0 = static_cast<int64_t>(tile) * kTileRows + kHalfRows * half;
+      const int n_valid = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(kHalfRows), a.n_rows - row0)));
       if (a.dense) {
-        // bootstrap: every score of this tile goes to the private area (zeros for rows past the end)
-        if (q_ok && n_mine + kTileRows <= a.cap_p) {
+        // bootstrap: every score of this half tile goes to the private area (zeros for rows past the end)
+        if (q_ok && n_mine + kHalfRows <= a.cap_p) {
           uint64_t* dst = my_list + n_mine;
 #pragma unroll
-          for (int c = 0; c < kTileRows; c += 2) {
+          for (int c = 0; c < kHalfRows; c += 2) {
             ulonglong2 o;
             o.x = (c < n_valid) ? pack_cand(__uint_as_float(v[c]), static_cast<uint32_t>(row0 + c)) : 0ull;
             o.y = (c + 1 < n_valid) ? pack_cand(__uint_as_float(v[c + 1]), static_cast<uint32_t>(row0 + c + 1)) : 0ull;
             *reinterpret_cast<ulonglong2*>(dst + c) = o;
           }
         }
-        n_mine += kTileRows;
-      } else {
-        // Branch-free filter: one predicate bit per score (a taken branch per score costs ~25 cycles
-        // with a single warp per scheduler — profiles/r01).  Hits are rare; they are handled per
-        // 32-column word in a warp-uniform loop over the columns any lane flagged, re-reading that
-        // single column from TMEM (a dynamic register index would demote v[] to local memory).
+        n_mine += kHalfRows;
+      } else if (__any_sync(0xffffffffu, any_ge32(v, tau))) {     // the common case is: no lane hits
+        // One predicate bit per score; hits are handled in a warp-uniform loop over the columns any lane
+        // flagged, re-reading that single column from TMEM (a dynamic register index would demote v[] to
+        // local memory) — or, for a busy word (loose thresholds early in a pass), by unrolled predicated stores.
+        uint32_t m = 0;
 #pragma unroll
-        for (int w = 0; w < kTileRows / 32; ++w) {
-          if (!__any_sync(0xffffffffu, any_ge32(v + 32 * w, tau))) continue;   // the common case: no lane hits
-          uint32_t m = 0;
+        for (int c = 0; c < kHalfRows; ++c) m |= (__uint_as_float(v[c]) >= tau) ? (1u << c) : 0u;
+        if (n_valid < kHalfRows) m &= (n_valid > 0) ? ((1u << n_valid) - 1u) : 0u;   // shard tail
+        uint32_t any = __reduce_or_sync(0xffffffffu, m);
+        if (__popc(any) > 6) {
+          if (m) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) m |= (__uint_as_float(v[32 * w + c]) >= tau) ? (1u << c) : 0u;
-          if (32 * w + 32 > n_valid) m &= (n_valid > 32 * w) ? ((1u << (n_valid - 32 * w)) - 1u) : 0u;  // shard tail
-          uint32_t any = __reduce_or_sync(0xffffffffu, m);
-          if (__popc(any) > 6) {
-            // Busy word (loose threshold, early in a pass): fully unrolled predicated stores — ~9
-            // instructions per column whether it hits or not, but no TMEM round trip per hit column.
-            if (m) {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                if ((m >> c) & 1u) {
-                  const int slot = n_mine + __popc(m & ((1u << c) - 1u));
-                  if (slot < a.cap_p)
-                    my_list[slot] = pack_cand(__uint_as_float(v[32 * w + c]), static_cast<uint32_t>(row0 + 32 * w + c));
-                  count_hit(v[32 * w + c]);
-                }
+            for (int c = 0; c < kHalfRows; ++c) {
+              if ((m >> c) & 1u) {
+                const int slot = n_mine + __popc(m & ((1u << c) - 1u));
+                if (slot < a.cap_p) my_list[slot] = pack_cand(__uint_as_float(v[c]), static_cast<uint32_t>(row0 + c));
+                count_hit(v[c]);
               }
-              n_mine += __popc(m);
             }
-          } else {
-            while (any) {   // rare: re-read the flagged column from TMEM (v[] must stay in registers)
-              const int c = __ffs(any) - 1;
-              any &= any - 1;
-              const uint32_t bits = tmem_ld_x1(lane_addr + kTmemColD + as * kTileRows + 32 * w + c);
-              tmem_ld_wait();
-              if ((m >> c) & 1u) {   // no atomics: the area is private to this thread
-                if (n_mine < a.cap_p) my_list[n_mine] = pack_cand(__uint_as_float(bits), static_cast<uint32_t>(row0 + 32 * w + c));
-                ++n_mine;
-                count_hit(bits);
-              }
+            n_mine += __popc(m);
+          }
+        } else {
+          while (any) {
+            const int c = __ffs(any) - 1;
+            any &= any - 1;
+            const uint32_t bits = tmem_ld_x1(col0 + c);
+            tmem_ld_wait();
+            if ((m >> c) & 1u) {   // no atomics: the area is private to this thread
+              if (n_mine < a.cap_p) my_list[n_mine] = pack_cand(__uint_as_float(bits), static_cast<uint32_t>(row0 + c));
+              ++n_mine;
+              count_hit(bits);
             }
           }
         }
@@ -547,7 +549,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     // follows k/rows_seen continuously, so ONE launch streams the whole shard after the bootstrap.
     float last[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     const long long t_start = clock64();
-    while (*epi_done_s < 4) {
+    while (*epi_done_s < kUmmaEpiWarps) {
       int qi = 0;
       for (int q = blockIdx.x; q < a.nq; q += gridDim.x, ++qi) {
         const uint32_t key0 = a.hkey0[q];

@@ -66,7 +66,7 @@ struct UmmaQsArgs {
   const int* hshift;          // [nq]
   const unsigned char* x16_bytes;   // base of the shadow (for the L2 prefetch)
   int64_t pf_limit_bytes;     // prefetches stay below this offset (end of the padded shadow rows)
-  int prefetch;               // D > 0: the producer keeps an L2 prefetch D tiles ahead of its ring; 0: off
+  int prefetch;               // D > 0: warp 3 keeps an L2 prefetch (LSU path) D tiles ahead of the producer; 0: off
   int dense_quarters;         // first tile of a CTA: lane quarters [0, dense_quarters) pass unfiltered
   int first_wait_cycles;      // the other quarters wait this long at most for every threshold to exist (0: no wait)
 };
@@ -146,7 +146,7 @@ __device__ __forceinline__ bool any_ge16(const uint32_t (&v)[16], const float (&
 //   warp 0 lane 0 : passage producer (TMA; both CTAs stream their own 128 rows of every tile)
 //   warp 1        : MMA issuer (leader CTA only; one elected lane)
 //   warp 2        : TMEM allocation, then lane 0 = query producer (TMA from L2)
-//   warp 3        : idle
+//   warp 3        : optional L2 prefetcher (LSU path), else idle
 //   warps 4..11   : epilogue — TMEM lane quarter (warp % 4), one passage row per thread; the two warps of a
 //                   quarter take alternate 16-query chunks of the row
 //   warp 12       : refresher — raises the global thresholds from the hit histogram and refreshes the
@@ -179,6 +179,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail_ptr + 16 * kQsMaxAStages + 16 * kQsMaxQStages + 8 + 32);
   volatile int* epi_done_s = reinterpret_cast<volatile int*>(tmem_ptr_s + 1);
   volatile int* tau_ready_s = reinterpret_cast<volatile int*>(tmem_ptr_s + 2);   // every query has a finite threshold
+  volatile int* prod_it_s = reinterpret_cast<volatile int*>(tmem_ptr_s + 3);     // tile iteration the passage producer is at
   float* tau_s = reinterpret_cast<float*>(tail_ptr + 512);               // [kQsMaxCols]
   int* cnt_s = reinterpret_cast<int*>(tail_ptr + 512 + 1024);            // [kQsMaxCols]
   uint32_t* hkey0_s = reinterpret_cast<uint32_t*>(tail_ptr + 512 + 2048);  // [kQsMaxCols]
@@ -215,7 +216,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
                  ::"r"(smem_u32(tmem_ptr_s)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x == 0) { *epi_done_s = 0; *tau_ready_s = 0; }
+  if (threadIdx.x == 0) { *epi_done_s = 0; *tau_ready_s = 0; *prod_it_s = 0; }
   for (int i = threadIdx.x; i < kQsMaxCols; i += kQsThreads) {
     tau_s[i] = (i < a.nq) ? a.tau[i] : INFINITY;     // padded query columns never hit
     cnt_s[i] = 0;
@@ -230,25 +231,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
   if (warp == 0 && lane == 0) {
     // ===================== passage producer =====================
     uint32_t stage = 0, phase = 0;
-    // L2 prefetch.  With the queries resident, 80 KB of ring per SM are too few bytes in flight to cover HBM
-    // latency at full bandwidth (measured: 5.9 TB/s with 5 stages vs 6.7 with 7).  A CTA's 128-row tile is ONE
-    // contiguous 192 KB region of the shadow (4 consecutive 32-row tiles x 12 K-blocks x 4 KB), so the
-    // producer asks L2 for one 16 KB slice of the tile `prefetch` rounds ahead with every stage it loads:
-    // the ring then only has to cover L2 latency, and the requests are spread evenly over the stream.
-    constexpr uint32_t kTileBytesCta = kQsTileRowsCta * kD * 2;     // 196,608
-    auto prefetch_slice = [&](int tile, int kb) {
-      const int64_t off = (static_cast<int64_t>(tile) * 2 + cta_rank) * kTileBytesCta + static_cast<int64_t>(kb) * kQsStageBytes;
-      if (tile < a.tile_end && off + kQsStageBytes <= a.pf_limit_bytes) l2_prefetch_bulk(a.x16_bytes + off, kQsStageBytes);
-    };
-    const int pfd = a.prefetch;
-    for (int d = 1; d < pfd; ++d)     // tiles nearer than the steady-state distance are requested up front
-      for (int kb = 0; kb < kNumKBlocks; ++kb) prefetch_slice(a.tile_begin + pair + d * npairs, kb);
-    for (int tile = a.tile_begin + pair; tile < a.tile_end; tile += npairs) {
+    int prod_it = 0;
+    for (int tile = a.tile_begin + pair; tile < a.tile_end; tile += npairs, ++prod_it) {
+      *prod_it_s = prod_it;       // progress mark for the L2 prefetch warp
       // shadow layout (common.cuh): this CTA's 128 rows are 4 consecutive 32-row tiles; K-block kb of
       // each is a contiguous 4 KB piece -> 4 TMA boxes per 16 KB stage (rows past the end: zero fill)
       const int t32 = (tile * 2 + static_cast<int>(cta_rank)) * (kQsTileRowsCta / kShadowTileRows);
       for (int kb = 0; kb < kNumKBlocks; ++kb) {
-        if (pfd) prefetch_slice(tile + pfd * npairs, kb);
         mbar_wait(bar_aempty + 8 * stage, phase ^ 1u, a.err);
         const uint32_t full_leader = mapa_u32(bar_afull + 8 * stage, 0);
         if (leader) mbar_arrive_expect_tx(bar_afull + 8 * stage, 2u * kQsStageBytes);
@@ -283,6 +272,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
           if (++stage == static_cast<uint32_t>(a.q_stages)) { stage = 0; phase ^= 1u; }
         }
       }
+    }
+  } else if (warp == 3 && a.prefetch > 0) {
+    // ===================== L2 prefetcher (optional) =====================
+    // With the queries resident, 80 KB of ring per SM are too few bytes in flight to cover HBM latency at
+    // full bandwidth (5 stages: 5.9 TB/s, 7 stages: 6.7).  Prefetching through the TMA unit (cp.async.bulk.
+    // prefetch) made things worse both times it was tried — the requests queue in front of the demand loads
+    // of the same unit.  This warp uses the LSU path instead: one `prefetch.global.L2` per 128-byte line of
+    // the CTA's tile `prefetch` rounds ahead (a tile is ONE contiguous 192 KB region of the shadow: 4
+    // consecutive 32-row tiles x 12 K-blocks x 4 KB), paced by the producer's progress mark.
+    constexpr int64_t kTileBytesCta = static_cast<int64_t>(kQsTileRowsCta) * kD * 2;     // 196,608
+    int it_pf = 0;
+    for (int tile = a.tile_begin + pair; tile < a.tile_end; tile += npairs, ++it_pf) {
+      while (it_pf > *prod_it_s + a.prefetch) __nanosleep(400);
+      if (it_pf <= *prod_it_s) continue;          // the producer is already there
+      const int64_t off = (static_cast<int64_t>(tile) * 2 + cta_rank) * kTileBytesCta;
+      if (off + kTileBytesCta > a.pf_limit_bytes) continue;
+      const unsigned char* base_g = a.x16_bytes + off;
+      for (int i = lane; i < static_cast<int>(kTileBytesCta / 128); i += 32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base_g + static_cast<int64_t>(i) * 128));
     }
   } else if (warp == 1 && leader) {
     // ===================== MMA issuer (leader CTA; the whole warp waits, one elected lane issues) =====

@@ -120,9 +120,10 @@ class FlatIPIndex:
     def reserve(self, n_per_shard: int) -> None:
         _lib.check(_lib.load().b2f_reserve(self._ensure(), int(n_per_shard)))
 
-    def add_flat_file(self, path: str, shard: int = 0, threads: int = 4):
+    def add_flat_file(self, path: str, shard: int = 0, threads: int = 0):
         """Stream one flat shard file (blocks.py format) into shard `shard` through pinned staging buffers
-        (b2f_add_flat_file); the stored passage offsets become the labels.  Returns (seconds, gigabytes).
+        (b2f_add_flat_file; threads = 0: the host's cores shared out over the shards); the stored passage
+        offsets become the labels.  Returns (seconds, gigabytes).
         Thread-safe across different shards: ctypes releases the GIL, one host thread per GPU keeps every
         PCIe link busy."""
         secs, gb = C.c_double(), C.c_double()

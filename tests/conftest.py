@@ -29,8 +29,9 @@ def gpu_count():
 def _built_library():
     """The CUDA library and the oracle's C restatement are built in-tree before any test runs."""
     from convdr_b200 import build
+    from oracle import build as oracle_build
     build.build_cuda()
-    build.build_oracle()
+    oracle_build.build_oracle()
     yield
 
 

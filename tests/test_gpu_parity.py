@@ -594,3 +594,51 @@ def test_native_flat_file_loader_streams_many_pieces(tmp_path):
     assert a.ntotal == 2 * n
     with pytest.raises(RuntimeError):
         a.add_flat_file(str(tmp_path / "missing.b2f"))
+
+
+def _synthetic_index(n, **opts):
+    idx = make_index("auto", None, **opts)
+    idx.reserve(n)
+    for a in range(0, n, 1 << 22):
+        idx.add_synthetic(min(1 << 22, n - a), first_row=a)
+    return idx
+
+
+def _check_against_full_size_oracle(D, I, Q, sel, k, n):
+    """fp64 truth of the selected queries over ALL n rows of the synthetic stream, regenerated on the host block by
+    block (oracle/flat_ip_c.c oracle_topk_synth_f64) — detects a missed row, unlike re-scoring the returned ones."""
+    Dt, It = c_oracle.topk_synth_f64(Q[sel], k, 0, n)
+    score_of = lambda qi, ids: synth.rows(np.asarray(ids).astype(np.uint64)).astype(np.float64) @ Q[sel[qi]].astype(np.float64)
+    r = flat_ip.compare(D[sel], I[sel], Dt, It, score_of, rtol=RTOL)
+    assert r["violations"] == 0, r
+    rel = np.abs(D[sel].astype(np.float64) - Dt) / np.maximum(np.abs(Dt), 1e-30)
+    assert rel.max() <= RTOL_TRUTH, rel.max()
+    return r
+
+
+def test_config2_shape_8p8M_rows_173_queries_top1000_against_the_full_size_oracle():
+    """BASELINE.json configs[1]: MS MARCO-sized 8,841,823 x 768, the CAsT-19 batch, top-1000 (what
+    data/gen_ranking_data.py consumes), single GPU.  At this size the gap near rank 1000 is ~1e-5 of the score:
+    where a margin or threshold bug would show first."""
+    n, k = 8_841_823, 1000
+    idx = _synthetic_index(n)
+    Q = c_oracle.synth_block(0, 173, stream=1)
+    D, I = idx.search(Q, k)
+    assert idx.stat("fallback_queries") == 0 and (np.diff(D, axis=1) <= 0).all()
+    _check_against_full_size_oracle(D, I, Q, [0, 21, 43, 86, 129, 150, 165, 172], k, n)
+    idx.close()
+
+
+def test_config3_shape_11p1M_rows_5571_queries_top100_against_the_full_size_oracle():
+    """BASELINE.json configs[2]: OR-QuAC-sized 11.1M x 768, all 5,571 test queries in one call (22 passes: 21 of
+    256 queries on the TS kernel, the last 195 on QS), top-100; a 16-query subset spread over the passes is
+    compared with the full-size oracle."""
+    n, k, nq = 11_100_000, 100, 5571
+    idx = _synthetic_index(n)
+    Q = c_oracle.synth_block(0, nq, stream=1)
+    D, I = idx.search(Q, k)
+    assert idx.stat("fallback_queries") == 0 and (np.diff(D, axis=1) <= 0).all()
+    assert (idx.stat("passes"), idx.stat("qs_passes")) == (22, 1)
+    sel = sorted(set(np.linspace(0, nq - 1, 16).astype(int).tolist()))
+    _check_against_full_size_oracle(D, I, Q, sel, k, n)
+    idx.close()
