@@ -464,9 +464,10 @@ def run_b2f_arm(args):
                      "clocks": samp2.stop() if rank == 0 else None}
 
     # ---- end-to-end timing through the public host-buffer API ----
+    q_pin_np = q_pin.numpy()       # the step's inputs live in pinned host memory (bench contract): uploaded from there
     def step_e2e():
         if world == 1:
-            return index.search(q_host, k)                 # faiss-style call: numpy in, numpy out
+            return index.search(q_pin_np, k)               # faiss-style call: numpy in, numpy out
         return sharded.search_host(q_host, k, device=dev)
     for _ in range(2):
         De, Ie = step_e2e()
@@ -709,6 +710,7 @@ def oracle_check_full_size(args, q_host, Dn, In, rank, n_queries: int = 16):
     from convdr_b200 import synth
     data_norm, data_shift = (28.0, 443) if args.data == "aniso" else (1.0, 0)
     sel = sorted(set(np.linspace(0, args.nq - 1, min(n_queries, args.nq)).astype(int).tolist()))
+    c_oracle.set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the other ranks are idle here
     t0 = time.perf_counter()
     Dt, It = c_oracle.topk_synth_f64(q_host[sel], args.k, 0, args.rows, seed=0, stream=0, norm=data_norm,
                                      mean_shift=data_shift)

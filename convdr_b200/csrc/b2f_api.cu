@@ -935,10 +935,11 @@ int finish_search(b2f_index* idx, Shard& S, const float* q_d, int64_t nq, int k,
                              cudaMemcpyDeviceToDevice, s));
     B2F_TRY(enqueue_pass(idx, S, plan, W.fbq, nullptr, W.qnorm /*unused: exact*/, W.qerr, nb, k, W.fbD, W.fbI, k, nullptr));
     for (int i = 0; i < nb; ++i) {
+      // cudaMemcpyDefault: D_d / I_d may be mapped pinned host memory (b2f_search writes results there directly)
       CU_TRY(cudaMemcpyAsync(D_d + bad[b0 + i] * k, W.fbD + static_cast<size_t>(i) * k, sizeof(float) * k,
-                             cudaMemcpyDeviceToDevice, s));
+                             cudaMemcpyDefault, s));
       CU_TRY(cudaMemcpyAsync(I_d + bad[b0 + i] * k, W.fbI + static_cast<size_t>(i) * k, sizeof(int64_t) * k,
-                             cudaMemcpyDeviceToDevice, s));
+                             cudaMemcpyDefault, s));
     }
   }
   CU_TRY(cudaStreamSynchronize(s));
@@ -1471,6 +1472,14 @@ int b2f_xchg_flush(b2f_index* idx) {
   return xchg_flush_deferred(idx);
 }
 
+// Page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) is addressable by the device
+// under unified addressing: copies from it need no staging, and kernels can store results straight into it.
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_host, int64_t* I_host) {
   B2F_TRY(check_args_search(idx, q_host, nq, k, D_host, I_host));
   if (nq == 0) return B2F_OK;
@@ -1481,74 +1490,73 @@ int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_
   const size_t d_off = static_cast<size_t>(round_up(static_cast<int64_t>(nq) * k * 4, 16));
   const size_t obytes = d_off + static_cast<size_t>(nq) * k * sizeof(int64_t);  // pinned layout [D | pad | I]
   Shard& S0 = idx->shards[0];
-  // stage the queries once in pinned memory, then upload to every shard
   CU_TRY(cudaSetDevice(S0.dev));
-  B2F_TRY(ensure_pin(S0, std::max(qbytes, obytes)));
-  std::memcpy(S0.ws.pin, q_host, qbytes);
+  // Host side of the call (the e2e path): queries are uploaded from the caller's buffer when it is page-locked,
+  // else through one pinned staging copy; results are written by the LAST kernel of the search (finalize /
+  // merge) straight into page-locked host memory over PCIe — the caller's arrays when they are page-locked,
+  // else the library's buffer followed by one memcpy — so no device-to-host copy operation is queued at all
+  // and the host waits exactly once.
+  const bool q_pinned = is_pinned_host(q_host);
+  const bool out_pinned = is_pinned_host(D_host) && is_pinned_host(I_host);
+  B2F_TRY(ensure_pin(S0, qbytes + obytes + 64));
+  char* pin = static_cast<char*>(S0.ws.pin);
+  const float* q_src = q_host;
+  if (!q_pinned) {
+    std::memcpy(pin, q_host, qbytes);
+    q_src = reinterpret_cast<const float*>(pin);
+  }
+  char* out_base = pin + round_up(static_cast<int64_t>(qbytes), 64);
+  float* outD = out_pinned ? D_host : reinterpret_cast<float*>(out_base);
+  int64_t* outI = out_pinned ? I_host : reinterpret_cast<int64_t*>(out_base + d_off);
   const int64_t per = nq * k;
-  if (G > 1) {   // gather area on the first device: parts [G][nq][k] + the merged result
+  if (G > 1) {   // gather area on the first device: parts [G][nq][k]
     Workspace& W = S0.ws;
-    if (per * (G + 1) > W.parts_cap) {
+    if (per * G > W.parts_cap) {
       dev_free(W.Dp); dev_free(W.Ip);
-      B2F_TRY(dev_alloc(&W.Dp, static_cast<size_t>(per) * (G + 1)));
-      B2F_TRY(dev_alloc(&W.Ip, static_cast<size_t>(per) * (G + 1)));
-      W.parts_cap = per * (G + 1);
+      B2F_TRY(dev_alloc(&W.Dp, static_cast<size_t>(per) * G));
+      B2F_TRY(dev_alloc(&W.Ip, static_cast<size_t>(per) * G));
+      W.parts_cap = per * G;
     }
   }
-  // Where shard g leaves its [nq,k] lists: a shard whose device can store into the first device's
-  // memory writes its part of the gather area directly (the last kernel of the search pushes the rows
-  // over NVLink as it produces them); otherwise its own buffer + a peer copy below.
-  auto part_D = [&](int g) { return (G > 1 && (g == 0 || idx->shards[g].peer_to_first)) ? S0.ws.Dp + per * g : idx->shards[g].ws.D; };
-  auto part_I = [&](int g) { return (G > 1 && (g == 0 || idx->shards[g].peer_to_first)) ? S0.ws.Ip + per * g : idx->shards[g].ws.I; };
+  // Where shard g leaves its [nq,k] lists.  One shard: the host buffer itself.  Several: a shard whose device
+  // can store into the first device's memory writes its part of the gather area directly (the last kernel of
+  // the search pushes the rows over NVLink as it produces them); otherwise its own buffer + a peer copy below.
+  auto part_D = [&](int g) { return G == 1 ? outD : ((g == 0 || idx->shards[g].peer_to_first) ? S0.ws.Dp + per * g : idx->shards[g].ws.D); };
+  auto part_I = [&](int g) { return G == 1 ? outI : ((g == 0 || idx->shards[g].peer_to_first) ? S0.ws.Ip + per * g : idx->shards[g].ws.I); };
   B2F_TRY(run_on_shards(idx, [&](int g) -> int {   // every device is enqueued by its own host thread
     Shard& S = idx->shards[g];
     CU_TRY(cudaSetDevice(S.dev));
     B2F_TRY(ensure_query_ws(S, nq, k));
-    CU_TRY(cudaMemcpyAsync(S.ws.q32, S0.ws.pin, qbytes, cudaMemcpyHostToDevice, S.stream));
+    CU_TRY(cudaMemcpyAsync(S.ws.q32, q_src, qbytes, cudaMemcpyHostToDevice, S.stream));
     return enqueue_search(idx, S, S.ws.q32, nq, k, part_D(g), part_I(g));
   }));
-  float* pinD = reinterpret_cast<float*>(S0.ws.pin);
-  int64_t* pinI = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(S0.ws.pin) + d_off);
   if (G == 1) {
-    // single shard: the download is enqueued behind the search, ONE synchronisation; only if a
-    // candidate list overflowed (rare) the affected queries are re-run and downloaded again
-    CU_TRY(cudaMemcpyAsync(pinD, S0.ws.D, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
-    CU_TRY(cudaMemcpyAsync(pinI, S0.ws.I, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
-    bool reran = false;
-    B2F_TRY(finish_search(idx, S0, S0.ws.q32, nq, k, S0.ws.D, S0.ws.I, 0, &reran));
-    if (reran) {
-      CU_TRY(cudaMemcpyAsync(pinD, S0.ws.D, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
-      CU_TRY(cudaMemcpyAsync(pinI, S0.ws.I, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
-      CU_TRY(cudaStreamSynchronize(S0.stream));
+    // ONE synchronisation; only if a candidate list overflowed (rare) the affected queries are re-run,
+    // their rows rewritten in place
+    B2F_TRY(finish_search(idx, S0, S0.ws.q32, nq, k, outD, outI, 0, nullptr));
+  } else {
+    for (int g = 0; g < G; ++g) {
+      Shard& S = idx->shards[g];
+      B2F_TRY(finish_search(idx, S, S.ws.q32, nq, k, part_D(g), part_I(g)));
     }
-    std::memcpy(D_host, pinD, sizeof(float) * nq * k);
-    std::memcpy(I_host, pinI, sizeof(int64_t) * nq * k);
-    return B2F_OK;
+    CU_TRY(cudaSetDevice(S0.dev));
+    Workspace& W = S0.ws;
+    for (int g = 1; g < G; ++g) {
+      Shard& S = idx->shards[g];
+      if (S.peer_to_first) continue;
+      CU_TRY(cudaMemcpyPeerAsync(W.Dp + per * g, S0.dev, S.ws.D, S.dev, sizeof(float) * per, S0.stream));
+      CU_TRY(cudaMemcpyPeerAsync(W.Ip + per * g, S0.dev, S.ws.I, S.dev, sizeof(int64_t) * per, S0.stream));
+    }
+    const int msb = merge_stage_bytes(G, k);
+    merge_kernel<<<static_cast<int>(nq), 256, msb, S0.stream>>>(W.Dp, W.Ip, G, nq, k, outD, outI, per, per, nullptr, msb > 0);
+    CU_TRY(cudaGetLastError());
+    idx->stats.launches += 1;
+    CU_TRY(cudaStreamSynchronize(S0.stream));
   }
-  for (int g = 0; g < G; ++g) {
-    Shard& S = idx->shards[g];
-    B2F_TRY(finish_search(idx, S, S.ws.q32, nq, k, part_D(g), part_I(g)));
+  if (!out_pinned) {
+    std::memcpy(D_host, outD, sizeof(float) * nq * k);
+    std::memcpy(I_host, outI, sizeof(int64_t) * nq * k);
   }
-  CU_TRY(cudaSetDevice(S0.dev));
-  Workspace& W = S0.ws;
-  for (int g = 1; g < G; ++g) {
-    Shard& S = idx->shards[g];
-    if (S.peer_to_first) continue;
-    CU_TRY(cudaMemcpyPeerAsync(W.Dp + per * g, S0.dev, S.ws.D, S.dev, sizeof(float) * per, S0.stream));
-    CU_TRY(cudaMemcpyPeerAsync(W.Ip + per * g, S0.dev, S.ws.I, S.dev, sizeof(int64_t) * per, S0.stream));
-  }
-  const int msb = merge_stage_bytes(G, k);
-  merge_kernel<<<static_cast<int>(nq), 256, msb, S0.stream>>>(W.Dp, W.Ip, G, nq, k, W.Dp + per * G, W.Ip + per * G, per, per,
-                                                              nullptr, msb > 0);
-  CU_TRY(cudaGetLastError());
-  idx->stats.launches += 1;
-  const float* Dres = W.Dp + per * G;
-  const int64_t* Ires = W.Ip + per * G;
-  CU_TRY(cudaMemcpyAsync(pinD, Dres, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
-  CU_TRY(cudaMemcpyAsync(pinI, Ires, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, S0.stream));
-  CU_TRY(cudaStreamSynchronize(S0.stream));
-  std::memcpy(D_host, pinD, sizeof(float) * nq * k);
-  std::memcpy(I_host, pinI, sizeof(int64_t) * nq * k);
   return B2F_OK;
 }
 

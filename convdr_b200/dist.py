@@ -236,9 +236,10 @@ class ShardedFlatIP:
         return D, I
 
     def search_host(self, q_host, k: int, device=None):
-        """End-to-end call with host buffers: pinned H2D of the queries, search, D2H of the result.
-        GPU ranks: upload, search, exchange, merge and download are all queued on the engine's stream
-        (persistent pinned staging buffers), ONE host wait."""
+        """End-to-end call with host buffers: pinned H2D of the queries, search, results in host memory.
+        GPU ranks: upload, search, exchange and merge are all queued on the engine's stream; the merge kernel
+        (the LAST kernel of the call) stores the [nq, k] results straight into pinned host memory over PCIe,
+        so no device-to-host copy is queued and the host waits exactly once."""
         if device is None or self.index is None:
             D, I = self.search(torch.from_numpy(q_host), k)
             return D.cpu().numpy(), I.cpu().numpy()
@@ -249,40 +250,35 @@ class ShardedFlatIP:
             self._hD = torch.empty((nq, k), dtype=torch.float32).pin_memory()
             self._hI = torch.empty((nq, k), dtype=torch.int64).pin_memory()
             self._dq = torch.empty((nq, q_host.shape[1]), dtype=torch.float32, device=device)
-            self._dD = torch.empty((nq, k), dtype=torch.float32, device=device)
-            self._dI = torch.empty((nq, k), dtype=torch.int64, device=device)
             self._hkey = key
         if getattr(self, "_ext", None) is None:
             self._ext = torch.cuda.ExternalStream(self.index.stream_ptr(0), device=device)
-        cur = torch.cuda.current_stream(device)
-        # The pinned staging tensors only ever meet torch's own stream (its host allocator records the
-        # streams a pinned block was used on and touches them again when the block is freed, possibly
-        # after the engine's stream is gone); the engine stream is ordered against it with events.
-        self._hq.numpy()[...] = q_host
+        # The pinned query tensor only ever meets torch's own stream (its host allocator records the streams a
+        # pinned block was used on); the engine stream is ordered behind the upload by search_async.  The
+        # pinned result tensors are only ever written by engine kernels and read after the wait below.
+        if q_host.ctypes.data != self._hq.data_ptr():
+            self._hq.numpy()[...] = q_host
         self._dq.copy_(self._hq, non_blocking=True)
 
-        def download():
+        def settle():
             if self.world > 1 and getattr(self, "_last_peer", False):
                 self.index.xchg_flush()              # the deferred merge joins the engine stream now, no wait
-            cur.wait_stream(self._ext)
-            self._hD.copy_(self._dD, non_blocking=True)
-            self._hI.copy_(self._dI, non_blocking=True)
-            cur.synchronize()                        # the one host wait: upload, search, exchange, merge, download
+            self._ext.synchronize()                  # the one host wait: upload, search, exchange, merge
             self.index.finish()                      # stream already idle: settles the overflow flags
 
-        self.search_async(self._dq, k, self._dD, self._dI)   # waits (on device) for the upload
-        download()
+        self.search_async(self._dq, k, self._hD, self._hI)   # waits (on device) for the upload; writes host memory
+        settle()
         # Rare: a candidate list overflowed; finish() re-ran those queries locally.  With several ranks the
-        # decision to repeat the exchange must be the same everywhere, so it only looks at the in-band
-        # marker every rank's merge saw (never at a rank-local counter).
+        # decision to repeat the exchange must be the same everywhere, so it only looks at the in-band marker
+        # every rank's merge saw (never at a rank-local counter).
         if self.world > 1:
             if self.index.stat("merge_saw_overflow") > 0:
                 D, I = self._search_cuda(self._dq, k)
-                self._dD.copy_(D); self._dI.copy_(I)
-                download()
+                self._hD.copy_(D)
+                self._hI.copy_(I)
+                torch.cuda.current_stream(device).synchronize()
         else:
             fb = self.index.stat("fallback_queries")      # cumulative over asynchronous searches
             if fb != getattr(self, "_fb_seen", 0.0):
-                self._fb_seen = fb
-                download()
+                self._fb_seen = fb                        # finish() rewrote the affected rows in place
         return self._hD.numpy().copy(), self._hI.numpy().copy()

@@ -49,6 +49,14 @@ def synth_block(first_row: int, n: int, seed: int = 0, stream: int = 0, norm: fl
     return out
 
 
+def set_threads(n: int) -> None:
+    """OpenMP threads of the C oracle (torchrun sets OMP_NUM_THREADS=1 for every rank)."""
+    lib = load()
+    lib.oracle_set_threads.restype = None
+    lib.oracle_set_threads.argtypes = [C.c_int]
+    lib.oracle_set_threads(int(n))
+
+
 def topk_synth_f64(Q: np.ndarray, k: int, first_row: int, n_rows: int, seed: int = 0, stream: int = 0,
                    norm: float = 1.0, mean_shift: int = 0):
     """float64 ground truth (D [nq,k], I [nq,k] global rows, order (score desc, row asc)) over rows
