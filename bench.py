@@ -468,7 +468,7 @@ def run_b2f_arm(args):
     def step_e2e():
         if world == 1:
             return index.search(q_pin_np, k)               # faiss-style call: numpy in, numpy out
-        return sharded.search_host(q_host, k, device=dev)
+        return sharded.search_host(q_pin_np, k, device=dev)
     for _ in range(2):
         De, Ie = step_e2e()
     barrier()

@@ -31,6 +31,7 @@ SYMBOLS = {
     "b2f_xchg_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b2f_search_xchg_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "b2f_xchg_flush": (C.c_int, [C.c_void_p]),
+    "b2f_search_xchg_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "b2f_merge_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int,
                                    C.c_void_p, C.c_void_p]),
     "b2f_reconstruct_n": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),

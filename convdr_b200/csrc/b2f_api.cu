@@ -1560,6 +1560,57 @@ int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_
   return B2F_OK;
 }
 
+// The whole end-to-end call of the one-process-per-GPU layout in ONE entry point: stage / upload the queries,
+// local search, NVLink push, wait + merge (storing the result straight into page-locked host memory), one
+// host wait, overflow protocol.  Collective: every rank calls it with the same nq, k.  (The Python layer
+// used to queue these pieces one ctypes / torch call at a time: ~0.25 ms of host time per search at a
+// 1.4 ms step.)
+int b2f_search_xchg_host(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_host, int64_t* I_host) {
+  B2F_TRY(check_args_search(idx, q_host, nq, k, D_host, I_host));
+  if (!idx->xchg.connected) return fail(B2F_ERR_INVALID, "exchange not connected (b2f_xchg_create / b2f_xchg_connect)");
+  if (nq == 0) return B2F_OK;
+  B2F_TRY(settle_pending(idx));
+  reset_stats(idx);
+  Shard& S = idx->shards[0];
+  CU_TRY(cudaSetDevice(S.dev));
+  const size_t qbytes = static_cast<size_t>(nq) * kD * 4;
+  const size_t d_off = static_cast<size_t>(round_up(static_cast<int64_t>(nq) * k * 4, 16));
+  const size_t obytes = d_off + static_cast<size_t>(nq) * k * sizeof(int64_t);
+  const bool q_pinned = is_pinned_host(q_host);
+  const bool out_pinned = is_pinned_host(D_host) && is_pinned_host(I_host);
+  B2F_TRY(ensure_pin(S, qbytes + obytes + 64));
+  B2F_TRY(ensure_query_ws(S, nq, k));
+  char* pin = static_cast<char*>(S.ws.pin);
+  const float* q_src = q_host;
+  if (!q_pinned) {
+    std::memcpy(pin, q_host, qbytes);
+    q_src = reinterpret_cast<const float*>(pin);
+  }
+  char* out_base = pin + round_up(static_cast<int64_t>(qbytes), 64);
+  float* outD = out_pinned ? D_host : reinterpret_cast<float*>(out_base);
+  int64_t* outI = out_pinned ? I_host : reinterpret_cast<int64_t*>(out_base + d_off);
+  CU_TRY(cudaMemcpyAsync(S.ws.q32, q_src, qbytes, cudaMemcpyHostToDevice, S.stream));
+  *idx->merge_flag_host = 0;
+  B2F_TRY(b2f_search_xchg_async(idx, S.ws.q32, nq, k, outD, outI, 0));
+  B2F_TRY(xchg_flush_deferred(idx));          // the merge of THIS step joins the stream now
+  B2F_TRY(b2f_search_finish(idx));            // the one host wait (+ local re-run of overflowed queries)
+  if (idx->merge_flag_host[1]) return fail(B2F_ERR_INTERNAL, "peer exchange timed out: a rank's part never arrived");
+  if (*idx->merge_flag_host) {
+    // some rank's list had overflowed when its part travelled (in-band marker, seen by every rank's merge):
+    // every rank pushes again — the owner with its re-run rows — and merges again
+    *idx->merge_flag_host = 0;
+    B2F_TRY(b2f_search_xchg_async(idx, S.ws.q32, nq, k, outD, outI, 1));
+    B2F_TRY(xchg_flush_deferred(idx));
+    B2F_TRY(b2f_search_finish(idx));
+    *idx->merge_flag_host = 0;
+  }
+  if (!out_pinned) {
+    std::memcpy(D_host, outD, sizeof(float) * nq * k);
+    std::memcpy(I_host, outI, sizeof(int64_t) * nq * k);
+  }
+  return B2F_OK;
+}
+
 int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
   if (!idx || !key) return fail(B2F_ERR_INVALID, "bad option arguments");
   B2F_TRY(settle_pending(idx));

@@ -244,6 +244,11 @@ class ShardedFlatIP:
             D, I = self.search(torch.from_numpy(q_host), k)
             return D.cpu().numpy(), I.cpu().numpy()
         nq = q_host.shape[0]
+        if self.world > 1 and getattr(self, "_peer", False) and nq <= self._peer_cap[0] and k <= self._peer_cap[1] \
+                and nq * k <= self._peer_cap[0] * self._peer_cap[1]:
+            # peer-memory exchange: the whole call is ONE entry point of the engine (upload, search, NVLink
+            # push, merge into page-locked host memory, one wait, overflow protocol)
+            return self.index.search_xchg_host(q_host, k)
         key = (nq, k, str(device))
         if getattr(self, "_hkey", None) != key:
             self._hq = torch.empty((nq, q_host.shape[1]), dtype=torch.float32).pin_memory()

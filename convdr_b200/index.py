@@ -218,6 +218,17 @@ class FlatIPIndex:
         _lib.check(_lib.load().b2f_search_xchg_async(self._ensure(), q.data_ptr(), q.shape[0], int(k), D.data_ptr(),
                                                      I.data_ptr(), 1 if repush_only else 0))
 
+    def search_xchg_host(self, x, k: int, D=None, I=None):
+        """Collective end-to-end search with host buffers (b2f_search_xchg_host): numpy in, numpy out; pass
+        page-locked arrays (e.g. views of torch pinned tensors) to skip the staging copies."""
+        x = self._as_rows(x, "x")
+        nq = x.shape[0]
+        if D is None:
+            D = np.empty((nq, int(k)), dtype=np.float32)
+            I = np.empty((nq, int(k)), dtype=np.int64)
+        _lib.check(_lib.load().b2f_search_xchg_host(self._ensure(), x.ctypes.data, nq, int(k), D.ctypes.data, I.ctypes.data))
+        return D, I
+
     def xchg_flush(self) -> None:
         """Enqueue the exchange merge that is still owed (deferred by one search), without waiting."""
         _lib.check(_lib.load().b2f_xchg_flush(self._ensure()))

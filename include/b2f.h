@@ -173,6 +173,14 @@ int b2f_xchg_create(b2f_index* idx, int rank, int world, int64_t max_nq, int max
 int b2f_xchg_connect(b2f_index* idx, const void* handles);
 int b2f_search_xchg_async(b2f_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
                           int64_t* I_dev, int repush_only);
+/* The same collective as ONE host-buffer call (the end-to-end path of the
+ * one-process-per-GPU layout): upload of q_host (straight from the caller's buffer
+ * when it is page-locked), local search, push, wait + merge — whose result rows are
+ * stored directly into page-locked host memory (the caller's arrays when they are
+ * page-locked, else a staging buffer + one memcpy) —, one host wait, and the overflow
+ * protocol (local re-run + collective re-push when any rank's list overflowed).     */
+int b2f_search_xchg_host(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_host,
+                         int64_t* I_host);
 /* The merge of an exchange step is enqueued one search later (the ranks are then
  * coupled with one step of slack instead of a barrier per search; option
  * "xchg_defer", default 1) or by b2f_search_finish.  b2f_xchg_flush enqueues a

@@ -5,8 +5,13 @@
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
+if [ "$3" = "fewtests" ]; then   # N GPU-minutes per minute: only the tests that need more than one GPU
+echo "=== multi-GPU tests ($N GPUs visible)"
+timeout 600 python -m pytest tests -q -m gpu --timeout 500 -rs -k "peer_memory or multi_gpu" > gpurun_out/r3m_tests_n$N.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/r3m_tests_n$N.log
+else
 echo "=== gpu tests (all, $N GPUs visible)"
 timeout 700 python -m pytest tests -q -m gpu --timeout 500 -rs > gpurun_out/r3m_tests_n$N.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/r3m_tests_n$N.log
+fi
 bench() { # tag, args...
   tag=$1; shift
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N "$@" > gpurun_out/r3m_${tag}_n$N.json 2> gpurun_out/r3m_${tag}_n$N.err; rc=$?
@@ -29,7 +34,7 @@ if [ "$2" = "more" ]; then
 bench aniso --steps 20 --warmup 5 --data aniso --inproc 0
 bench c3 --config c3 --steps 5 --warmup 3 --inproc 0
 bench c2 --config c2 --steps 20 --warmup 3 --inproc 0
-bench c5 --config c5
+bench c5 --config c5 --sweep-nq 1,8,64,173,256,1024,4096,16384
 echo "=== loader, $N GPUs"
-timeout 400 python tools/load_bench.py $N 1500000 > gpurun_out/r3m_load_n$N.json 2> gpurun_out/r3m_load_n$N.err; echo "rc=$?"; cat gpurun_out/r3m_load_n$N.json; tail -3 gpurun_out/r3m_load_n$N.err
+timeout 400 python tools/load_bench.py $N 1000000 > gpurun_out/r3m_load_n$N.json 2> gpurun_out/r3m_load_n$N.err; echo "rc=$?"; cat gpurun_out/r3m_load_n$N.json; tail -3 gpurun_out/r3m_load_n$N.err
 fi
