@@ -719,7 +719,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     finalize_kernel<<<nqp, kFinThreads, static_cast<size_t>(P + PS) * sizeof(uint64_t), s>>>(
         W.cand[0], W.gath, W.cnt, C, k, W.margin, plan.S, plan.cap_a, n_areas, W.cnt2, W.ovf, ovf_dst, q32p,
         S.x32, S.segs_d, static_cast<int>(S.segs.size()), S.has_ids ? S.idmap : nullptr, D_out, I_out, out_stride, P,
-        W.tau);
+        W.tau, S.mu);
     CU_TRY(cudaGetLastError());
     st.launches += 1;
     st.passes += 1;
@@ -816,7 +816,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     finalize_kernel<<<nqp, kFinThreads, static_cast<size_t>(P + PS) * sizeof(uint64_t), s>>>(
         W.cand[cur], W.gath, W.cnt, C, k, W.margin, plan.S, cap_h, n_areas, W.cnt2, W.ovf, ovf_dst, q32p,
         S.x32, S.segs_d, static_cast<int>(S.segs.size()), S.has_ids ? S.idmap : nullptr, D_out, I_out, out_stride, P,
-        idx->tighten ? W.tau : nullptr);
+        idx->tighten ? W.tau : nullptr, S.mu);
     CU_TRY(cudaGetLastError());
     st.launches += 1;
     st.passes += 1;

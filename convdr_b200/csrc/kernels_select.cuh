@@ -578,10 +578,12 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
     const int* __restrict__ ovf, int* __restrict__ ovf_out, const float* __restrict__ q32,
     const float* __restrict__ x32, const Seg* __restrict__ segs, int nseg, const int64_t* __restrict__ idmap,
     float* __restrict__ D_out, int64_t* __restrict__ I_out, int64_t out_stride, int P,
-    const float* __restrict__ tau_low /* [nq] lower bounds of the survivor thresholds, or null */) {
+    const float* __restrict__ tau_low /* [nq] lower bounds of the survivor thresholds, or null */,
+    const float* __restrict__ mu /* [768] centre of the shard: approximate scores are q.(p - mu) */) {
   extern __shared__ __align__(16) uint64_t fin_buf[];   // [P] gathered list, then the survivors
   __shared__ FinSmem sm;
   __shared__ __align__(16) float Qs[kD];
+  __shared__ double q_dot_mu;
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint64_t* bufB = fin_buf + P;
@@ -643,6 +645,13 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
     }
     return kmin;   // order-preserving key of the smallest exact score this warp produced
   };
+  // The approximate scores live in CENTRED space (s~ ~ q.p - q.mu), the exact ones do
+  // not: T is moved into centred space with c = q.mu, evaluated in fp64 (products of fp32 values are exact,
+  // the 768-term sum is good to ~1e-13 relative; 1e-9 |c| of slack covers it many times over).
+  if (warp == 0) {
+    const double c = warp_butterfly_sum(lane_partial_f64(q4, reinterpret_cast<const float4*>(mu), lane));
+    if (lane == 0) q_dot_mu = c;
+  }
   const bool two_rounds = f.kth_key != 0xffffffffu && margin[q] > 0.f;
   const uint64_t recA = two_rounds ? (static_cast<uint64_t>(f.kth_key) << 32) : T;   // T == 0 with fewer than k records
   const int mA_all = collect(recA, ~0ull, 0);
@@ -654,8 +663,9 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
   __syncthreads();
   int m2_all = mA_all;
   if (two_rounds && mA_all <= S) {
-    const float t_exact = key2f(sm.digit);                               // min exact score of round A
-    const float lowB = __fsub_rd(t_exact, __fmul_ru(margin[q], 0.5f));   // T - eps, rounded down
+    const double t_exact = static_cast<double>(key2f(sm.digit));         // min exact score of round A (uncentred)
+    const double c = q_dot_mu;
+    const float lowB = __double2float_rd(t_exact - c - static_cast<double>(__fmul_ru(margin[q], 0.5f)) - 1e-9 * fabs(c));   // (T - q.mu) - eps
     const uint64_t recB = max(T, static_cast<uint64_t>(fkey(lowB)) << 32);   // never below the one-round window
     __syncthreads();
     const int mB_all = collect(recB, recA, mA);
