@@ -757,6 +757,9 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       a.max_pairs = n_areas; a.cnt2 = W.cnt2; a.tau = W.tau; a.ovf = W.ovf; a.err = W.err;
       a.tighten = idx->tighten; a.tighten_adaptive = idx->tighten_adaptive; a.k = k; a.margin = W.margin; a.hist = W.hist; a.hkey0 = W.hkey0; a.hshift = W.hshift;
       const int pairs = std::min(S.max_pairs, te - tb);
+      // wait for the first thresholds after the first tile: only when that tile's rows can place them (about half of
+      // pairs * 64 rows score above the histogram floor) and the shard is long enough to be worth it
+      a.first_wait_cycles = (one_launch && N >= 8ll * pairs * kTileRows && 4ll * k <= static_cast<int64_t>(pairs) * kTileRows) ? 100000 : 0;
       {
         ProfScope ps(idx, S, 0);
         umma_score_select_kernel<<<2 * pairs, kUmmaThreads, kUmmaSmemBytes, s>>>(tmap_p, a);

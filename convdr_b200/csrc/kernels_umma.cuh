@@ -24,8 +24,9 @@
 
 namespace b2f {
 
-constexpr int kUmmaThreads = 384;                // 4 service warps + 8 epilogue warps (two per TMEM lane quarter)
+constexpr int kUmmaThreads = 416;                // 4 service warps + 8 epilogue warps (two per TMEM lane quarter) + refresher
 constexpr int kUmmaEpiWarps = 8;
+constexpr int kUmmaRefresherWarp = 12;           // highest warp id: scheduled ahead of the epilogue warps of its quarter
 constexpr int kBlockK = 64;                    // bf16 per K-block = 128 bytes (one swizzle span)
 constexpr int kNumKBlocks = kD / kBlockK;      // 12
 constexpr int kTileRowsCta = kShadowTileRows;  // passage rows per CTA per tile (32)
@@ -83,6 +84,8 @@ struct UmmaArgs {
                               //     relative age costs a bounded fraction of extra hits whatever the moment,
                               //     and a launch needs ~50 polling rounds instead of thousands
   int k;
+  int first_wait_cycles;      // one-launch schedule: after its first tile an epilogue thread waits this long at most
+                              // for its query's first threshold (0: no wait)
   const float* margin;        // [nq] 2*eps of the prefilter
   unsigned int* hist;         // [nq][kHistStride], initialised by pass_init_kernel / bootstrap_select_kernel
   const uint32_t* hkey0;      // [nq] key of the bootstrap's k-th best approximate score (0xffffffff: none yet)
@@ -307,12 +310,13 @@ __device__ __forceinline__ bool any_ge32(const uint32_t* v, float tau) {
 //   warp 0 lane 0 : TMA producer (both CTAs stream their own 32 rows of every tile)
 //   warp 1 lane 0 : MMA issuer (leader CTA only)
 //   warp 2        : TMEM allocation / release
-//   warp 3        : refresher (in-kernel threshold tightening)
+//   warp 3        : idle
 //   warps 4..11   : load the queries into TMEM, then epilogue — thread (rank, lane) of warp w owns query
 //                   128*rank + 32*(w%4) + lane and, of every 64-row tile, the 32 rows of half (w-4)/4: two
 //                   threads per query, each with its own private list area (hit handling is per-thread
 //                   instruction overhead in a warp that the scheduler cannot hide: two warps per TMEM lane
 //                   quarter halve it and overlap each other's latencies)
+//   warp 12       : refresher (in-kernel threshold tightening)
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     umma_score_select_kernel(const __grid_constant__ CUtensorMap tmap_p, const UmmaArgs a) {
@@ -411,7 +415,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
         if (++stage == kNumStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + kUmmaEpiWarps) {
     // ===================== queries -> TMEM, then epilogue =====================
     const int ew = warp & 3;
     const int half = (warp - 4) >> 2;      // which 32 rows of every 64-row tile / which half of the query columns to load
@@ -466,6 +470,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     int it = 0;
     for (int tile = a.tile_begin + pair; tile < a.tile_end; tile += npairs, ++it) {
       const uint32_t as = static_cast<uint32_t>(it) % kAccStages, aph = (static_cast<uint32_t>(it) / kAccStages) & 1u;
+      if (it == 1 && live && a.first_wait_cycles > 0) {
+        // The first tile of every pair passed unfiltered (thresholds start at -inf): together those rows place
+        // every query's first threshold.  Waiting for it here (bounded) instead of streaming on keeps the
+        // private areas from filling with rows the final selection would throw away — at full clocks a pair
+        // finishes a tile every ~0.8 us, the first threshold takes a few us to travel.
+        const long long t0 = clock64();
+        while (*tau_g == -INFINITY && clock64() - t0 < a.first_wait_cycles) __nanosleep(256);
+      }
       float tau_new = tau;
       if (live) tau_new = *tau_g;            // issued before the wait: the L2 latency hides behind it
       mbar_wait(bar_tfull + 8 * as, aph, a.err);
@@ -536,7 +548,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     }
     __syncwarp();
     if (lane == 0) atomicAdd(const_cast<int*>(epi_done_s), 1);
-  } else if (warp == 3 && a.tighten && !a.dense) {
+  } else if (warp == kUmmaRefresherWarp && a.tighten && !a.dense) {
     // ===================== refresher: in-kernel threshold tightening =====================
     // While the stream runs, this otherwise idle warp keeps reading, for the queries assigned to
     // this CTA (q = blockIdx.x, + gridDim.x, ...), the histogram of hits above the bootstrap's k-th
@@ -599,8 +611,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
         }
       }
       unsigned int pause = static_cast<unsigned int>(a.tighten);
-      if (a.tighten_adaptive) {
-        const long long age_ns = (clock64() - t_start) >> 1;     // cycles -> ns at ~2 GHz; only a pacing hint
+      const long long age_ns = (clock64() - t_start) >> 1;       // cycles -> ns at ~2 GHz; only a pacing hint
+      if (age_ns < 30000) pause = min(pause, 500u);              // start of the pass: epilogue threads wait for the first thresholds
+      else if (a.tighten_adaptive) {
         pause = static_cast<unsigned int>(min(max(static_cast<long long>(pause), age_ns >> 2), 50000ll));
       }
       __nanosleep(pause);
