@@ -4,6 +4,9 @@ peer-memory exchange kernels must give bit-identical results, equal to a single 
 AND to the oracle's float64 ground truth (ids identical; ties cannot occur outside the planted block,
 where the oracle's (score desc, index asc) order is the engine's total order too)."""
 import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch
@@ -72,11 +75,22 @@ def main():
                 for _ in range(6)]
         for D, I in outs:
             sh.search_async(q, 20, D, I)
-        assert sh.finish()
+        clean = sh.finish()
         Df, If = full.search(q.cpu().numpy(), 20)
-        for D, I in outs:
+        if clean:
+            for D, I in outs:
+                np.testing.assert_array_equal(I.cpu().numpy(), If)
+                np.testing.assert_array_equal(D.cpu().numpy(), Df)
+        else:
+            # Some query ranks the 5000 identical rows inside the margin of its 20th score on the owning rank (a
+            # matter of the seed and of the shard size): finish() says so on EVERY rank, and the documented
+            # protocol is to repeat those searches synchronously.
+            D, I = sh.search(q, 20)
             np.testing.assert_array_equal(I.cpu().numpy(), If)
             np.testing.assert_array_equal(D.cpu().numpy(), Df)
+        agree = [None] * world
+        dist.all_gather_object(agree, bool(clean))
+        assert len(set(agree)) == 1, agree            # the verdict of finish() is collective
         # host-buffer path (one host wait; the 173-query batch contains two planted overflowing queries -> redo branch)
         for nq, kk, seed in ((37, 100, 2), (173, 100, 3), (37, 100, 2)):
             qh = synth.block(0, nq, seed=seed, stream=1)
@@ -101,4 +115,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import sys
+        import traceback
+        print(f"XCHG_WORKER_FAILED rank {os.environ.get('RANK')}\n" + traceback.format_exc(), flush=True)
+        sys.stdout.flush()
+        raise

@@ -504,7 +504,7 @@ def test_peer_memory_exchange_equals_nccl_exchange(gpu_count):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "_xchg_worker.py")]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=500)
-    assert res.returncode == 0 and f"XCHG_OK {world}" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+    assert res.returncode == 0 and f"XCHG_OK {world}" in res.stdout, res.stdout[-6000:] + res.stderr[-3000:]
 
 
 def test_shard_with_a_block_of_identical_rows_overflows_for_some_queries_only():

@@ -36,5 +36,5 @@ bench c3 --config c3 --steps 5 --warmup 3 --inproc 0
 bench c2 --config c2 --steps 20 --warmup 3 --inproc 0
 bench c5 --config c5 --sweep-nq 1,8,64,173,256,1024,4096,16384
 echo "=== loader, $N GPUs"
-timeout 400 python tools/load_bench.py $N 1000000 > gpurun_out/r3m_load_n$N.json 2> gpurun_out/r3m_load_n$N.err; echo "rc=$?"; cat gpurun_out/r3m_load_n$N.json; tail -3 gpurun_out/r3m_load_n$N.err
+timeout 400 python tools/load_bench.py $N 500000 > gpurun_out/r3m_load_n$N.json 2> gpurun_out/r3m_load_n$N.err; echo "rc=$?"; cat gpurun_out/r3m_load_n$N.json; tail -3 gpurun_out/r3m_load_n$N.err
 fi
