@@ -2,7 +2,7 @@
 (scratch) into profiles/ (tracked), and condense the `ncu --set full` captures into
 profiles/ncu_summary.json (what bench.py reads for `roofline.traffic`).
 
-    python tools/collect_profiles.py [tag]        # tag defaults to r01s2 (round 1, session 2)
+    python tools/collect_profiles.py [tag]        # tag defaults to r02 (round 2)
 """
 import csv
 import json
@@ -25,7 +25,7 @@ COPY = {
     "launches_4p8M.csv": "{tag}_launches_4p8M_rows.csv",
     "sweep_8p8M_k100.json": "{tag}_sweep_8p8M_k100.json",
     "sweep_8p8M_k1000.json": "{tag}_sweep_8p8M_k1000.json",
-    "sweep_11p1M_k100.json": "{tag}_sweep_11p1M_k100.json",
+    "bench_c2.json": "{tag}_bench_c2_8p8M_k1000_1gpu.json",
     "bench_n2.json": "{tag}_bench_38p6M_2gpu.json",
     "bench_n4.json": "{tag}_bench_38p6M_4gpu.json",
     "bench_n8.json": "{tag}_bench_38p6M_8gpu.json",
@@ -72,26 +72,35 @@ def summarise(rep, rows_streamed, label, tag):
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01s2"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     os.makedirs(PROF, exist_ok=True)
     for src, dst in COPY.items():
         p = os.path.join(OUT, src)
         if os.path.exists(p) and os.path.getsize(p) > 0:
             shutil.copyfile(p, os.path.join(PROF, dst.format(tag=tag)))
             print("copied", src, "->", dst.format(tag=tag))
+    path = os.path.join(PROF, "ncu_summary.json")
     summary = {}
-    for rep, rows, label in (("prof_umma_headline.ncu-rep", 38636520, "umma_ts_38p6M_rows"),
+    if os.path.exists(path):
+        with open(path) as fh:
+            summary = json.load(fh)          # earlier rounds' captures stay (the TS kernel's are round 1's)
+    fresh = {}
+    for rep, rows, label in (("prof_qs_headline.ncu-rep", 38636520, "umma_qs_38p6M_rows"),
+                             ("prof_qs_4p8M.ncu-rep", 4829565, "umma_qs_4p8M_rows"),
+                             ("prof_umma_headline.ncu-rep", 38636520, "umma_ts_38p6M_rows"),
                              ("prof_umma_4p8M.ncu-rep", 4829565, "umma_ts_4p8M_rows")):
         p = os.path.join(OUT, rep)
         if os.path.exists(p):
-            summary[label] = summarise(p, rows, label, tag)
-            print(label, json.dumps(summary[label]))
-    if summary:
-        # bench.py reads umma_score_select_kernel.dram_bytes_per_row (the headline-size capture)
-        head = summary.get("umma_ts_38p6M_rows") or next(iter(summary.values()))
-        summary["umma_score_select_kernel"] = head
-        with open(os.path.join(PROF, "ncu_summary.json"), "w") as fh:
-            json.dump(summary, fh, indent=1)
+            fresh[label] = summarise(p, rows, label, tag)
+            print(label, json.dumps(fresh[label]))
+    summary.update(fresh)
+    # bench.py reads <kernel name>.dram_bytes_per_row (the headline-size capture of each scoring kernel)
+    if "umma_qs_38p6M_rows" in summary or "umma_qs_4p8M_rows" in summary:
+        summary["umma_qs_score_select_kernel"] = summary.get("umma_qs_38p6M_rows") or summary["umma_qs_4p8M_rows"]
+    if "umma_ts_38p6M_rows" in summary:
+        summary["umma_score_select_kernel"] = summary["umma_ts_38p6M_rows"]
+    with open(path, "w") as fh:
+        json.dump(summary, fh, indent=1)
 
 
 if __name__ == "__main__":

