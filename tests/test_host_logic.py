@@ -159,3 +159,39 @@ def test_bench_reference_arm_prints_one_contract_json_line():
     assert j["value"] > 0 and j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and "sample" in j["cpu_baseline"]
     assert j["metric"].startswith("exact top-100 queries/sec") and j["config"]["workload"]
+
+
+def test_bench_configs_follow_baseline_json():
+    """bench.py --config cN sets the shape BASELINE.json's configs[N-1] names; c4 is the headline metric."""
+    import importlib
+    sys.argv, saved = ["bench.py", "--config", "c3"], sys.argv
+    try:
+        bench = importlib.import_module("bench")
+        args = bench.parse_args()
+        assert (args.rows, args.nq, args.k) == (11_100_000, 5571, 100)
+        assert "11.1M" in bench.metric_name(args)
+        sys.argv = ["bench.py"]
+        args = bench.parse_args()
+        assert (args.rows, args.nq, args.k) == (38_636_520, 173, 100) and bench.metric_name(args) == bench.METRIC
+        sys.argv = ["bench.py", "--config", "c2"]
+        args = bench.parse_args()
+        assert (args.rows, args.nq, args.k) == (8_841_823, 173, 1000)
+    finally:
+        sys.argv = saved
+
+
+def test_flat_shard_rows_and_fallback_loader(tmp_path):
+    from convdr_b200 import blocks
+    P = np.arange(5 * 768, dtype=np.float32).reshape(5, 768)
+    path = blocks.write_flat_shard(str(tmp_path / (blocks.FLAT_NAME % 0)), P, np.arange(5, dtype=np.int64) * 2)
+    assert blocks.flat_shard_rows(path) == 5
+
+    class Fake:                       # no add_flat_file: the chunked add_with_ids path
+        def __init__(self):
+            self.rows, self.ids = [], []
+        def add_with_ids(self, x, ids):
+            self.rows.append(x.copy()); self.ids.append(ids.copy())
+    f = Fake()
+    assert blocks.load_flat_into(f, [path], chunk_rows=2) == 5
+    np.testing.assert_array_equal(np.concatenate(f.rows), P)
+    np.testing.assert_array_equal(np.concatenate(f.ids), np.arange(5) * 2)

@@ -196,3 +196,19 @@ def test_eval_rank_dedup_keeps_first_occurrences_in_rank_order():
     assert pids[0].tolist() == [10, 11, 12, 0, 0] and counts[0] == 3          # only the first 5 entries are read
     assert scores[0].tolist() == [.9, .7, .5, 0.0, 0.0]
     assert pids[1].tolist() == [13, 12, 11, 10, 0] and counts[1] == 4         # -1 wraps to the last offset (pid 11)
+
+
+def test_full_size_oracle_equals_materialised_truth_and_synth_twins_agree_with_mean_shift():
+    """oracle_topk_synth_f64 (rows regenerated block by block, never materialised) == truth_fp64 over the
+    materialised rows, for isotropic rows and for rows with a common mean; host twins bit-identical."""
+    from convdr_b200 import synth
+    for kw in (dict(), dict(norm=28.0, mean_shift=443)):
+        P = c_oracle.synth_block(1000, 30000, seed=5, **kw)
+        np.testing.assert_array_equal(P[:500], synth.block(1000, 500, seed=5, **kw))
+        Q = c_oracle.synth_block(0, 6, seed=5, stream=1, **kw)
+        D, I = c_oracle.topk_synth_f64(Q, 25, 1000, 30000, seed=5, **kw)
+        Dt, It = flat_ip.truth_fp64(Q, P, 25)
+        np.testing.assert_array_equal(I, It + 1000)
+        np.testing.assert_allclose(D, Dt, rtol=1e-12)
+    D, I = c_oracle.topk_synth_f64(Q, 10, 0, 4)           # fewer rows than k: padded like the index
+    assert (I[:, 4:] == -1).all() and np.isneginf(D[:, 4:]).all()

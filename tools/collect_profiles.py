@@ -26,9 +26,6 @@ COPY = {
     "sweep_8p8M_k100.json": "{tag}_sweep_8p8M_k100.json",
     "sweep_8p8M_k1000.json": "{tag}_sweep_8p8M_k1000.json",
     "bench_c2.json": "{tag}_bench_c2_8p8M_k1000_1gpu.json",
-    "bench_n2.json": "{tag}_bench_38p6M_2gpu.json",
-    "bench_n4.json": "{tag}_bench_38p6M_4gpu.json",
-    "bench_n8.json": "{tag}_bench_38p6M_8gpu.json",
 }
 SCALE = {"Tbyte": 1e12, "Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 TIME = {"s": 1e3, "ms": 1.0, "us": 1e-3, "ns": 1e-6}
@@ -86,9 +83,7 @@ def main():
             summary = json.load(fh)          # earlier rounds' captures stay (the TS kernel's are round 1's)
     fresh = {}
     for rep, rows, label in (("prof_qs_headline.ncu-rep", 38636520, "umma_qs_38p6M_rows"),
-                             ("prof_qs_4p8M.ncu-rep", 4829565, "umma_qs_4p8M_rows"),
-                             ("prof_umma_headline.ncu-rep", 38636520, "umma_ts_38p6M_rows"),
-                             ("prof_umma_4p8M.ncu-rep", 4829565, "umma_ts_4p8M_rows")):
+                             ("prof_qs_4p8M.ncu-rep", 4829565, "umma_qs_4p8M_rows")):
         p = os.path.join(OUT, rep)
         if os.path.exists(p):
             fresh[label] = summarise(p, rows, label, tag)
