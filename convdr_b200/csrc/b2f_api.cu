@@ -191,6 +191,7 @@ struct Shard {
   std::vector<Seg> segs;
   Seg* segs_d = nullptr;
   int segs_d_cap = 0;
+  bool segs_dirty = true;            // host segment list changed since it was last uploaded
   Workspace ws;
   Prof prof;
   Stats stats;
@@ -367,6 +368,8 @@ int ensure_capacity(b2f_index* idx, Shard& S, int64_t need) {
 }
 
 int upload_segs(Shard& S) {
+  if (!S.segs_dirty) return B2F_OK;   // one small H2D copy less on the stream of every search
+  S.segs_dirty = false;
   const int n = static_cast<int>(S.segs.size());
   if (n > S.segs_d_cap) {
     dev_free(S.segs_d);
@@ -378,6 +381,7 @@ int upload_segs(Shard& S) {
 }
 
 void push_seg(Shard& S, int64_t local_start, int64_t count, int64_t global_start) {
+  S.segs_dirty = true;
   if (!S.segs.empty()) {
     Seg& b = S.segs.back();
     if (b.local_start + b.count == local_start && b.global_start + b.count == global_start) {
@@ -1265,6 +1269,7 @@ int b2f_reset(b2f_index* idx) {
     CU_TRY(cudaStreamSynchronize(S.stream));
     S.n = 0;
     S.segs.clear();
+    S.segs_dirty = true;
     S.has_ids = false;
     CU_TRY(cudaMemsetAsync(S.maxnorm2, 0, 4 * sizeof(unsigned int), S.stream));
     CU_TRY(cudaMemsetAsync(S.mu, 0, kD * sizeof(float), S.stream));
@@ -1320,13 +1325,13 @@ int b2f_search_finish(b2f_index* idx) {
 
 int b2f_merge_device(b2f_index* idx, const float* D_parts_dev, const int64_t* I_parts_dev, int n_parts,
                      int64_t nq, int k, float* D_dev, int64_t* I_dev) {
-  if (!idx || n_parts < 1 || nq < 0 || k < 1 || !D_parts_dev || !I_parts_dev || !D_dev || !I_dev)
-    return fail(B2F_ERR_INVALID, "bad merge arguments");
+  if (!idx || n_parts < 1 || n_parts > kXchgMaxWorldMerge || nq < 0 || k < 1 || !D_parts_dev || !I_parts_dev || !D_dev || !I_dev)
+    return fail(B2F_ERR_INVALID, "bad merge arguments (1..64 parts)");
   if (nq == 0) return B2F_OK;
   Shard& S = idx->shards[0];
   CU_TRY(cudaSetDevice(S.dev));
   const int msb = merge_stage_bytes(n_parts, k);
-  merge_kernel<<<static_cast<int>(nq), 256, msb, S.stream>>>(D_parts_dev, I_parts_dev, n_parts, nq, k, D_dev, I_dev,
+  merge_kernel<<<static_cast<int>(nq), merge_threads(n_parts, k), msb, S.stream>>>(D_parts_dev, I_parts_dev, n_parts, nq, k, D_dev, I_dev,
                                                              nq * k, nq * k, nullptr, msb > 0);
   CU_TRY(cudaGetLastError());
   idx->stats.launches += 1;
@@ -1336,7 +1341,7 @@ int b2f_merge_device(b2f_index* idx, const float* D_parts_dev, const int64_t* I_
 
 int b2f_merge_packed_device_async(b2f_index* idx, const void* parts_dev, int n_parts, int64_t part_bytes,
                                   int64_t i_offset_bytes, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
-  if (!idx || n_parts < 1 || nq < 0 || k < 1 || !parts_dev || !D_dev || !I_dev || part_bytes % 8 != 0 ||
+  if (!idx || n_parts < 1 || n_parts > kXchgMaxWorldMerge || nq < 0 || k < 1 || !parts_dev || !D_dev || !I_dev || part_bytes % 8 != 0 ||
       i_offset_bytes % 8 != 0 || i_offset_bytes < nq * k * 4 || part_bytes < i_offset_bytes + nq * k * 8)
     return fail(B2F_ERR_INVALID, "bad packed merge arguments");
   if (nq == 0) return B2F_OK;
@@ -1344,7 +1349,7 @@ int b2f_merge_packed_device_async(b2f_index* idx, const void* parts_dev, int n_p
   CU_TRY(cudaSetDevice(S.dev));
   const char* base = static_cast<const char*>(parts_dev);
   const int msb = merge_stage_bytes(n_parts, k);
-  merge_kernel<<<static_cast<int>(nq), 256, msb, S.stream>>>(
+  merge_kernel<<<static_cast<int>(nq), merge_threads(n_parts, k), msb, S.stream>>>(
       reinterpret_cast<const float*>(base), reinterpret_cast<const int64_t*>(base + i_offset_bytes), n_parts, nq, k,
       D_dev, I_dev, part_bytes / 4, part_bytes / 8, idx->merge_flag_dev, msb > 0);
   CU_TRY(cudaGetLastError());
@@ -1407,7 +1412,7 @@ static int xchg_launch_merge(b2f_index* idx, unsigned int seq, int64_t nq, int k
   {
     ProfScope ps(idx, S, 2);
     const int msb = merge_stage_bytes(X.world, k);
-    xchg_merge_kernel<<<static_cast<int>(nq), 256, msb, S.stream>>>(
+    xchg_merge_kernel<<<static_cast<int>(nq), merge_threads(X.world, k), msb, S.stream>>>(
         X.local + static_cast<size_t>(slot) * X.world * X.part_cap,
         reinterpret_cast<const unsigned int*>(X.local + X.flags_off) + slot * X.world, seq, X.world,
         static_cast<int64_t>(X.part_cap), i_off, nq, k, D_dev, I_dev, idx->merge_flag_dev, idx->merge_flag_dev + 1,
@@ -1551,7 +1556,7 @@ int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_
       CU_TRY(cudaMemcpyPeerAsync(W.Ip + per * g, S0.dev, S.ws.I, S.dev, sizeof(int64_t) * per, S0.stream));
     }
     const int msb = merge_stage_bytes(G, k);
-    merge_kernel<<<static_cast<int>(nq), 256, msb, S0.stream>>>(W.Dp, W.Ip, G, nq, k, outD, outI, per, per, nullptr, msb > 0);
+    merge_kernel<<<static_cast<int>(nq), merge_threads(G, k), msb, S0.stream>>>(W.Dp, W.Ip, G, nq, k, outD, outI, per, per, nullptr, msb > 0);
     CU_TRY(cudaGetLastError());
     idx->stats.launches += 1;
     CU_TRY(cudaStreamSynchronize(S0.stream));

@@ -11,6 +11,7 @@
 namespace b2f {
 
 constexpr int kSelThreads = 256;
+constexpr int kXchgMaxWorldMerge = 64;   // lists one merge handles (ranks of the exchange / shards of an index)
 constexpr int kSortCap = 2048;  // == B2F_MAX_K
 constexpr int kTightenBuckets = 512;  // == kHistBuckets of kernels_umma.cuh
 constexpr int kTightenStride = kTightenBuckets + kTightenBuckets / 16;  // == kHistStride: [512 fine][32 coarse] per query
@@ -748,23 +749,36 @@ __device__ __forceinline__ void merge_body(const float* Dp, const int64_t* Ip, i
   auto ld_score = [&](int g, int i) -> float {
     return staged ? sD[g * k + i] : __ldcg(Dp + static_cast<int64_t>(g) * strideD + q * k + i);
   };
+  // valid prefix of every list (lists are padded at the END with id = -1, or id = -2 in slot 0 for a pending
+  // re-run): the binary searches below then only ever read scores
+  __shared__ int n_valid_s[kXchgMaxWorldMerge];
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    int lo = 0, hi = k;
+    while (lo < hi) {                       // first index whose id is negative
+      const int mid = (lo + hi) >> 1;
+      if (ld_id(g, mid) >= 0) lo = mid + 1; else hi = mid;
+    }
+    n_valid_s[g] = lo;
+    if (ld_id(g, 0) == -2 && saw_overflow != nullptr) *saw_overflow = 1;   // a shard's list overflowed: result pending its re-run
+  }
+  __syncthreads();
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     const int g = e / k, i = e - g * k;
+    if (i >= n_valid_s[g]) continue;
     const int64_t id = ld_id(g, i);
-    if (id == -2 && saw_overflow != nullptr) *saw_overflow = 1;   // a shard's list overflowed: result pending its re-run
-    if (id < 0) continue;
+    if (id < 0) continue;                   // the marker row of a pending re-run
     atomicAdd(total_valid_s, 1);
     const float s = ld_score(g, i);
     int rank = i;
     for (int g2 = 0; g2 < G; ++g2) {
       if (g2 == g) continue;
       // count valid elements of list g2 that precede (s): score > s, or == s when g2 < g
-      int lo = 0, hi = k;
+      int lo = 0, hi = n_valid_s[g2];
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const bool valid = ld_id(g2, mid) >= 0;
         const float s2 = ld_score(g2, mid);
-        const bool before = valid && (s2 > s || (s2 == s && g2 < g));
+        const bool before = s2 > s || (s2 == s && g2 < g);
         if (before) lo = mid + 1; else hi = mid;
       }
       rank += lo;
@@ -782,12 +796,14 @@ __device__ __forceinline__ void merge_body(const float* Dp, const int64_t* Ip, i
 }
 
 constexpr int kMergeStageMaxBytes = 96 * 1024;
+// threads of a merge block: lists of a few hundred entries take 256; k = 1000 over 8 ranks is 8000 entries per query
+inline int merge_threads(int G, int k) { return static_cast<int64_t>(G) * k > 2048 ? 1024 : 256; }
 inline int merge_stage_bytes(int G, int k) {   // dynamic shared memory of the merge kernels (0: lists stay in L2)
   const int64_t b = static_cast<int64_t>(G) * k * 12;
   return b <= kMergeStageMaxBytes ? static_cast<int>(b) : 0;
 }
 
-__global__ void __launch_bounds__(256) merge_kernel(const float* Dp, const int64_t* Ip, int G, int64_t nq,
+__global__ void __launch_bounds__(1024) merge_kernel(const float* Dp, const int64_t* Ip, int G, int64_t nq,
                                                     int k, float* __restrict__ D, int64_t* __restrict__ I,
                                                     int64_t strideD, int64_t strideI,
                                                     int* __restrict__ saw_overflow /* mapped host int or null */,
@@ -841,7 +857,7 @@ __global__ void __launch_bounds__(256) xchg_push_kernel(const uint4* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(256) xchg_merge_kernel(const char* __restrict__ parts /* [world][part_cap] of this parity */,
+__global__ void __launch_bounds__(1024) xchg_merge_kernel(const char* __restrict__ parts /* [world][part_cap] of this parity */,
                                                          const unsigned int* flags /* [world] of this parity */,
                                                          unsigned int seq, int world, int64_t part_cap, int64_t i_off,
                                                          int64_t nq, int k, float* __restrict__ D, int64_t* __restrict__ I,
