@@ -1332,7 +1332,7 @@ int b2f_merge_device(b2f_index* idx, const float* D_parts_dev, const int64_t* I_
   CU_TRY(cudaSetDevice(S.dev));
   const int msb = merge_stage_bytes(n_parts, k);
   merge_kernel<<<static_cast<int>(nq), merge_threads(n_parts, k), msb, S.stream>>>(D_parts_dev, I_parts_dev, n_parts, nq, k, D_dev, I_dev,
-                                                             nq * k, nq * k, nullptr, msb > 0);
+                                                             nq * k, nq * k, nullptr, merge_mode(n_parts, k));
   CU_TRY(cudaGetLastError());
   idx->stats.launches += 1;
   CU_TRY(cudaStreamSynchronize(S.stream));
@@ -1351,7 +1351,7 @@ int b2f_merge_packed_device_async(b2f_index* idx, const void* parts_dev, int n_p
   const int msb = merge_stage_bytes(n_parts, k);
   merge_kernel<<<static_cast<int>(nq), merge_threads(n_parts, k), msb, S.stream>>>(
       reinterpret_cast<const float*>(base), reinterpret_cast<const int64_t*>(base + i_offset_bytes), n_parts, nq, k,
-      D_dev, I_dev, part_bytes / 4, part_bytes / 8, idx->merge_flag_dev, msb > 0);
+      D_dev, I_dev, part_bytes / 4, part_bytes / 8, idx->merge_flag_dev, merge_mode(n_parts, k));
   CU_TRY(cudaGetLastError());
   idx->stats.launches += 1;
   return B2F_OK;
@@ -1416,7 +1416,7 @@ static int xchg_launch_merge(b2f_index* idx, unsigned int seq, int64_t nq, int k
         X.local + static_cast<size_t>(slot) * X.world * X.part_cap,
         reinterpret_cast<const unsigned int*>(X.local + X.flags_off) + slot * X.world, seq, X.world,
         static_cast<int64_t>(X.part_cap), i_off, nq, k, D_dev, I_dev, idx->merge_flag_dev, idx->merge_flag_dev + 1,
-        msb > 0);
+        merge_mode(X.world, k));
   }
   CU_TRY(cudaGetLastError());
   idx->stats.launches += 1;
@@ -1556,7 +1556,7 @@ int b2f_search(b2f_index* idx, const float* q_host, int64_t nq, int k, float* D_
       CU_TRY(cudaMemcpyPeerAsync(W.Ip + per * g, S0.dev, S.ws.I, S.dev, sizeof(int64_t) * per, S0.stream));
     }
     const int msb = merge_stage_bytes(G, k);
-    merge_kernel<<<static_cast<int>(nq), merge_threads(G, k), msb, S0.stream>>>(W.Dp, W.Ip, G, nq, k, outD, outI, per, per, nullptr, msb > 0);
+    merge_kernel<<<static_cast<int>(nq), merge_threads(G, k), msb, S0.stream>>>(W.Dp, W.Ip, G, nq, k, outD, outI, per, per, nullptr, merge_mode(G, k));
     CU_TRY(cudaGetLastError());
     idx->stats.launches += 1;
     CU_TRY(cudaStreamSynchronize(S0.stream));
