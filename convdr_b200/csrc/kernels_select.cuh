@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(kFinThreads, 2) finalize_kernel(
 // valid (score, part, position) becomes one key  fkey(score) << 32 | ~(g*k + i),  so a descending sort orders
 // by (score desc, part asc, position asc) — the reference's `>=` merge rule — and the first k keys are the
 // result; ids are fetched for those k only.  One bitonic sort of <= 8192 keys replaces (G-1) binary searches
-// per record (measured 41 us -> a few us per launch at G = 8, k = 100; 153 -> ~15 us at k = 1000).
+// per record (measured 41 -> 18 us per launch at G = 8, k = 100; two lists stay on rank-by-counting: 7 vs 8 us).
 __device__ __forceinline__ void merge_sort_body(const float* Dp, const int64_t* Ip, int G, int64_t q, int k,
                                                 float* __restrict__ D, int64_t* __restrict__ I, int64_t strideD,
                                                 int64_t strideI, int* saw_overflow, unsigned char* stage_smem) {
@@ -856,7 +856,7 @@ inline int merge_threads(int G, int k) { return static_cast<int64_t>(G) * k > 20
 inline int merge_mode(int G, int k) {
   int64_t p2 = 32;
   while (p2 < static_cast<int64_t>(G) * k) p2 <<= 1;
-  if (p2 * 8 <= kMergeStageMaxBytes) return 2;
+  if (G >= 4 && p2 * 8 <= kMergeStageMaxBytes) return 2;   // rank-by-counting costs (G-1) searches per record: fine for 2-3 lists
   return static_cast<int64_t>(G) * k * 12 <= kMergeStageMaxBytes ? 1 : 0;
 }
 inline int merge_stage_bytes(int G, int k) {   // dynamic shared memory of the merge kernels
