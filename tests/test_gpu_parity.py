@@ -642,3 +642,29 @@ def test_config3_shape_11p1M_rows_5571_queries_top100_against_the_full_size_orac
     sel = sorted(set(np.linspace(0, nq - 1, 16).astype(int).tolist()))
     _check_against_full_size_oracle(D, I, Q, sel, k, n)
     idx.close()
+
+
+def test_page_locked_host_buffers_are_used_in_place():
+    """b2f_search with page-locked arrays: queries are uploaded straight from the caller's buffer and the last
+    kernel stores the result rows straight into the caller's arrays (no staging copies); same bits as the
+    pageable path.  Also through a 2-shard... single-shard index with explicit ids and an overflowing query
+    (re-run rows are rewritten in place)."""
+    import ctypes as C
+    import torch
+    from convdr_b200 import _lib
+    P = c_oracle.synth_block(0, 40000, seed=81)
+    P[30000:35000] = P[30000]                     # 5000 identical rows: the planted query overflows and is re-run
+    Q = c_oracle.synth_block(0, 37, seed=81, stream=1)
+    Q[5] = P[30000]
+    idx = make_index("auto", P)
+    D0, I0 = idx.search(Q, 50)                    # pageable numpy in / out
+    assert idx.stat("fallback_queries") >= 1
+    qp = torch.from_numpy(Q).pin_memory()
+    Dp = torch.empty((37, 50), dtype=torch.float32).pin_memory()
+    Ip = torch.empty((37, 50), dtype=torch.int64).pin_memory()
+    Dp.fill_(-1.0); Ip.fill_(-7)
+    _lib.check(_lib.load().b2f_search(idx._ensure(), C.c_void_p(qp.data_ptr()), 37, 50, C.c_void_p(Dp.data_ptr()),
+                                      C.c_void_p(Ip.data_ptr())))
+    np.testing.assert_array_equal(Ip.numpy(), I0)
+    np.testing.assert_array_equal(Dp.numpy(), D0)
+    check_against_oracle(D0, I0, P, Q, 50, also_fp32_oracle=False)
