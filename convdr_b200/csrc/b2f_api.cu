@@ -1,13 +1,15 @@
 // b2f_api.cu — host side of the engine behind the C ABI declared in include/b2f.h.
 //
 // One b2f_index owns one shard per device: the fp32 rows (for exact rescoring and the SIMT
-// engine), their bf16 shadow (streamed by the tensor engine), the norm bound of the shard, and a
-// per-shard workspace.  A search is a fixed sequence of kernels per query pass:
+// engine), the shard's centre, the bf16 shadow of the centred rows (streamed by the tensor engine),
+// the norm bounds of the shard, and a per-shard workspace.  A search is a fixed sequence of kernels:
 //
-//   prep_queries -> margin -> [score(dense) -> refresh] -> { score(filter) -> refresh }* -> final
+//   prep_queries -> per pass of <= 256 queries: pass_init -> score+select (ONE launch) -> finalize
 //
-// where "score" is either umma_score_select_kernel (tcgen05) or scan_kernel (SIMT).  There is no
-// CPU arithmetic anywhere on this path; without a CUDA device every entry point fails.
+// where score+select is umma_qs_score_select_kernel (<= 208 queries) or umma_score_select_kernel
+// (tcgen05, both), with the phased schedules (dense bootstrap / refresh between phases) kept for the
+// SIMT scan_kernel and as A/B options.  There is no CPU arithmetic anywhere on this path; without a
+// CUDA device every entry point fails.
 #include "../../include/b2f.h"
 
 #include <cuda.h>

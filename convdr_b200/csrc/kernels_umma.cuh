@@ -3,9 +3,13 @@
 //   queries  : bf16, loaded ONCE per launch into TMEM (tcgen05.st) — the A operand of every MMA
 //   passages : bf16 shadow tiles  HBM --TMA (contiguous 16 KB, 128B swizzle)--> 14-stage smem ring
 //   scores   : tcgen05.mma cta_group::2 (A from TMEM, B from smem) --> TMEM accumulator
-//   select   : tcgen05.ld --> one QUERY per epilogue thread, threshold in a register,
-//              survivors appended to a (query, CTA pair)-private area of the candidate list:
-//              no atomics, no shared memory, no cross-thread traffic
+//   select   : tcgen05.ld --> one (QUERY, half tile) per epilogue thread (8 epilogue warps), threshold in a
+//              register, one predicate-chained compare per score; survivors appended to a private area of
+//              the candidate list per (query, CTA pair, half tile): no atomics, no shared memory, no
+//              cross-thread traffic
+//
+// TS variant of the tensor engine: the kernel of passes with 209..256 queries (the full passes of large
+// batches); smaller passes take the QS variant (kernels_umma_qs.cuh), whose MMA shape follows the batch.
 //
 // One CTA pair (2 SMs) holds up to 256 queries (128 TMEM lanes per CTA, the MMA M dimension) and
 // walks tiles of 64 passage rows (32 per CTA, the MMA N dimension; two accumulator stages of 64

@@ -1,23 +1,25 @@
-// kernels_umma_qs.cuh — tensor-core scoring engine, "streamed queries" variant (sm_100a).
+// kernels_umma_qs.cuh — tensor-core scoring engine, QS variant: the queries on the MMA N side (sm_100a).
 //
-//   passages : bf16 shadow tiles  HBM --TMA (128B swizzle)--> deep smem ring                : A operand
-//   queries  : bf16, one 64-column K-block per ring stage, re-read from L2 for every passage tile
-//              (the whole batch is <= 384 KB: always L2-resident); optionally the first R K-blocks
-//              stay resident in shared memory                                              : B operand
-//   scores   : tcgen05.mma cta_group::2, M = 256 passage rows, N = query count rounded up to 16
-//   select   : tcgen05.ld --> one PASSAGE ROW per epilogue thread, per-query thresholds in shared
-//              memory, hits appended to a (query, CTA)-private list area (shared-memory counters, no
-//              global atomics) and counted in the tightening histogram; an otherwise idle warp keeps
-//              raising the thresholds while the stream runs (ONE launch streams the whole shard)
+//   passages : bf16 shadow tiles  HBM --TMA (128B swizzle)--> shared-memory ring of 16 KB stages   : A operand
+//   queries  : bf16, N = batch rounded up to 16 (176 for 173 queries: no padded lanes); the first R
+//              K-blocks (default: all 12) stay resident in shared memory, the others are re-read from L2
+//              for every passage tile through their own shallow ring                               : B operand
+//   scores   : tcgen05.mma cta_group::2, M = 256 passage rows per CTA pair, fp32 accumulators in TMEM (x2)
+//   select   : tcgen05.ld --> one PASSAGE ROW per epilogue thread, 8 epilogue warps; per-query thresholds in
+//              shared memory, ONE predicate-chained compare per score; hits appended to a (query, CTA)-private
+//              list area (shared-memory counters, no global atomics) and counted in the tightening histogram;
+//              a dedicated warp keeps raising the thresholds while the stream runs (ONE launch per pass)
 //
 // Why this variant exists: with the queries as the A operand in TMEM
 // (kernels_umma.cuh) every MMA issues M = 256 query lanes, so 173 queries pay for 256 and the kernel is
 // tensor-bound at 0.75-0.80 of HBM once the board's power cap pulls the SM clock to ~1.1-1.3 GHz.  With
-// the queries on the N side the MMA shape follows the batch (N = 176: 31 % fewer tensor cycles), but the
-// B operand must live in shared memory: 135 KB per CTA for 173 queries, which left the round-1 variant a
-// 5-stage passage ring — too few bytes in flight to cover HBM latency.  Here the queries are streamed
-// next to the passages instead (11 KB per 16 KB passage stage, from L2), through their own shallow ring
-// (L2 latency only), so the passage ring keeps 10-11 stages = 160-176 KB in flight per SM.
+// the queries on the N side the MMA shape follows the batch (N = 176: 31 % fewer tensor cycles and joules),
+// but the B operand must live in shared memory: 135 KB per CTA for 173 queries, which leaves a 5-stage
+// passage ring (80 KB in flight per SM).  Streaming the query K-blocks from L2 instead (R < 12) buys a ring of
+// up to 11 stages at the price of 11 KB of L2->SM traffic per 16 KB passage stage; measured (DESIGN.md
+// section 3) every split lands within 2 % at 173 queries and the fully resident layout wins in sustained,
+// power-capped runs, so R = 12 is the default and the streamed path serves batches too large to stay
+// resident.  What made this orientation pay at all was the epilogue: see any_ge16 below.
 //
 // Replaces the arithmetic of `index.search` (reference drivers/run_convdr_inference.py:182).
 #pragma once
@@ -93,11 +95,6 @@ inline QsPlan umma_qs_plan(int n_cols, int resident_kb, int q_stages) {
     }
     --resident_kb;   // too many resident K-blocks for this batch size: stream more of them
   }
-}
-
-// Ask L2 to fetch `bytes` (multiple of 16) of global memory; no destination, no completion to wait for.
-__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ float4 lds_volatile_f4(uint32_t addr) {
