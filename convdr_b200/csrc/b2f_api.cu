@@ -765,6 +765,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
       const int pairs = std::min(S.max_pairs, te - tb);
       // wait for the first thresholds after the first tile: only when that tile's rows can place them (about half of
       // pairs * 64 rows score above the histogram floor) and the shard is long enough to be worth it
+      a.count_exact_lower_bound = one_launch ? 1 : 0;
       a.first_wait_cycles = (one_launch && N >= 8ll * pairs * kTileRows && 4ll * k <= static_cast<int64_t>(pairs) * kTileRows) ? 100000 : 0;
       {
         ProfScope ps(idx, S, 0);

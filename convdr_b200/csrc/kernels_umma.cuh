@@ -88,6 +88,10 @@ struct UmmaArgs {
                               //     relative age costs a bounded fraction of extra hits whatever the moment,
                               //     and a launch needs ~50 polling rounds instead of thousands
   int k;
+  int count_exact_lower_bound; // 1 (one-launch schedule): hits are counted at s~ - eps, a lower bound of the EXACT score,
+                              //   so "k hits at or above edge e" bounds the k-th exact score itself and tau = e - eps;
+                              // 0 (phased schedules, whose histogram is seeded with raw approximate keys): count at
+                              //   s~, tau = e - 2 eps
   int first_wait_cycles;      // one-launch schedule: after its first tile an epilogue thread waits this long at most
                               // for its query's first threshold (0: no wait)
   const float* margin;        // [nq] 2*eps of the prefilter
@@ -462,8 +466,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
     uint64_t* my_list = a.cand + static_cast<int64_t>(q_ok ? q : 0) * a.C + a.S + static_cast<int64_t>(area) * a.cap_p;
     int n_mine = 0;   // entries this thread appended for (query q, this pair)
     // count a hit in the tightening histogram (fire-and-forget RED; hits are rare)
+    const float eps_cnt = (live && a.count_exact_lower_bound) ? __fmul_ru(a.margin[q], 0.5f) : 0.f;
     auto count_hit = [&](uint32_t bits) {
-      const uint32_t key = fkey(__uint_as_float(bits));
+      const uint32_t key = fkey(__fsub_rd(__uint_as_float(bits), eps_cnt));
       if (key >= hkey0) {
         const uint32_t b = min(static_cast<uint32_t>(kHistBuckets - 1), (key - hkey0) >> hshift);
         atomicAdd(my_hist + b, 1u);
@@ -605,7 +610,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
         if (lane == 0) {
           const uint64_t edge = static_cast<uint64_t>(key0) + (static_cast<uint64_t>(b) << a.hshift[q]);
           if (edge <= 0xff7fffffull) {         // a finite score key
-            const float t = __fsub_rd(key2f(static_cast<uint32_t>(edge)), a.margin[q]);
+            const float t = __fsub_rd(key2f(static_cast<uint32_t>(edge)),
+                                      a.count_exact_lower_bound ? __fmul_ru(a.margin[q], 0.5f) : a.margin[q]);
             const float prev = (qi < 4) ? last[qi] : *reinterpret_cast<volatile float*>(a.tau + q);
             if (t > prev) {
               *reinterpret_cast<volatile float*>(a.tau + q) = t;

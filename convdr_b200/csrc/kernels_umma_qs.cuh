@@ -344,7 +344,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
       if (pass) {
         const int slot = s0 + __popc(b & lt_mask);
         if (slot < a.cap_p) area0[static_cast<int64_t>(qc) * a.C + slot] = pack_cand(__uint_as_float(bits), row);
-        const uint32_t key = fkey(__uint_as_float(bits));
+        // counted at s~ - eps: a lower bound of the row's EXACT (centred) score, so that "k hits at or above
+        // bucket edge e" bounds the k-th best exact score itself and the threshold is e - eps, not e - 2 eps
+        const uint32_t key = fkey(__fsub_rd(__uint_as_float(bits), __fmul_ru(__ldg(a.margin + qc), 0.5f)));
         const uint32_t k0 = hkey0_s[qc];
         if (key >= k0) {
           const uint32_t hb = min(static_cast<uint32_t>(kHistBuckets - 1), (key - k0) >> __ldg(a.hshift + qc));
@@ -423,8 +425,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
   } else if (warp == kQsRefresherWarp) {
     // ===================== refresher: in-kernel threshold tightening =====================
     // Same scheme as the TS variant (kernels_umma.cuh): for the queries assigned to this CTA, read the
-    // histogram of hits, find the highest bucket b with >= k hits at or above it and publish
-    // tau[q] = edge(b) - 2*eps; additionally copy ALL current thresholds into this CTA's shared memory,
+    // histogram of hits (counted at s~ - eps), find the highest bucket b with >= k hits at or above it and
+    // publish tau[q] = edge(b) - eps; additionally copy ALL current thresholds into this CTA's shared memory,
     // where the epilogue threads (one passage row each, all queries) read them.
     float last[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     const long long t_start = clock64();
@@ -466,7 +468,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
           if (lane == 0) {
             const uint64_t edge = static_cast<uint64_t>(key0) + (static_cast<uint64_t>(b) << a.hshift[q]);
             if (edge <= 0xff7fffffull) {         // a finite score key
-              const float t = __fsub_rd(key2f(static_cast<uint32_t>(edge)), a.margin[q]);
+              const float t = __fsub_rd(key2f(static_cast<uint32_t>(edge)), __fmul_ru(a.margin[q], 0.5f));   // e - eps
               const float prev = (qi < 4) ? last[qi] : *reinterpret_cast<volatile float*>(a.tau + q);
               if (t > prev) {
                 *reinterpret_cast<volatile float*>(a.tau + q) = t;
