@@ -668,3 +668,29 @@ def test_page_locked_host_buffers_are_used_in_place():
     np.testing.assert_array_equal(Ip.numpy(), I0)
     np.testing.assert_array_equal(Dp.numpy(), D0)
     check_against_oracle(D0, I0, P, Q, 50, also_fp32_oracle=False)
+
+
+@pytest.mark.parametrize("n_parts", [2, 5, 8])
+def test_merge_kernels_keep_the_tie_order_across_parts(n_parts):
+    """Exact ties across parts (the same rows planted in several parts): the merged order must be (score desc,
+    part asc, position asc) — the reference's `>=` merge rule (:218) — for the rank-by-counting merge (2-3 parts)
+    and for the sort-mode merge (4+ parts)."""
+    import torch
+    P = c_oracle.synth_block(0, 8000 * n_parts, seed=91)
+    Q = c_oracle.synth_block(0, 9, seed=91, stream=1)
+    _, I0 = flat_ip.knn_inner_product(Q, P, 4)
+    for g in range(1, n_parts):                       # query 0's best rows reappear in every part
+        P[8000 * g + 17:8000 * g + 21] = P[I0[0, :4]]
+    whole = make_index("auto", P)
+    Dw, Iw = whole.search(Q, 30)
+    qd = torch.from_numpy(Q).cuda()
+    parts = []
+    for g in range(n_parts):
+        sub = make_index("auto")
+        sub.add_with_ids(P[8000 * g:8000 * (g + 1)], np.arange(8000 * g, 8000 * (g + 1), dtype=np.int64))
+        parts.append(sub.search_device(qd, 30))
+    Dm, Im = whole.merge_device(torch.stack([p[0] for p in parts]).contiguous(),
+                                torch.stack([p[1] for p in parts]).contiguous())
+    np.testing.assert_array_equal(Im.cpu().numpy(), Iw)
+    np.testing.assert_array_equal(Dm.cpu().numpy(), Dw)
+    assert (np.diff(Dw[0, :4 * n_parts]) == 0).sum() >= n_parts - 1      # the planted ties are really there
