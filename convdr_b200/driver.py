@@ -82,12 +82,21 @@ def search_resident(ann_data_dir, index, query_embedding, topN, max_blocks: int 
         if flat:
             load_flat_into(index, flat)
         else:
+            import os
+            n_files = 0
+            while n_files < max_blocks and os.path.exists(os.path.join(ann_data_dir, EMB_NAME % n_files)):
+                n_files += 1
             n_blocks = 0
             for block_id in range(max_blocks):
                 try:
                     emb, embid = load_block(ann_data_dir, block_id)
                 except FileNotFoundError:
                     break
+                if n_blocks == 0 and n_files > 1 and hasattr(index, "reserve"):
+                    # the blocks of one generation run have (nearly) equal sizes (strided split, utils/util.py:422-424):
+                    # size every shard once instead of regrowing it with a device-to-device copy per block
+                    shards = getattr(index, "num_shards", 1)
+                    index.reserve(-(-(emb.shape[0] + 1) * n_files // shards) + 1)
                 index.add_with_ids(emb, np.asarray(embid, dtype=np.int64))
                 n_blocks += 1
             if n_blocks == 0:
