@@ -25,14 +25,13 @@ def gpu_count():
     return _gpu_count()
 
 
-@pytest.fixture(scope="session", autouse=True)
-def _built_library():
-    """The CUDA library and the oracle's C restatement are built in-tree before any test runs."""
+def pytest_sessionstart(session):
+    """The CUDA library and the oracle's C restatement are built in-tree before COLLECTION (test modules bind
+    the library at import time), so a fresh clone runs without a separate build step."""
     from convdr_b200 import build
     from oracle import build as oracle_build
     build.build_cuda()
     oracle_build.build_oracle()
-    yield
 
 
 def pytest_collection_modifyitems(config, items):
