@@ -17,6 +17,7 @@ SYMBOLS = {
     "b2f_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
     "b2f_add_flat_file": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double),
                                     C.POINTER(C.c_double)]),
+    "b2f_write_flat_file": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
     "b2f_rank_dedup_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2f_add_synthetic": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64,

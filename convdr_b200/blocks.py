@@ -189,6 +189,19 @@ def load_flat_into(index, paths, chunk_rows: int = 1 << 18, rank: int = 0, world
     return added
 
 
+def save_index_to_flat(index, out_dir: str) -> list:
+    """One flat shard file per device-resident shard of `index` (`passage_shard_{s}.b2f`), written straight from
+    device memory; `load_flat_into` restores the same shards.  The writer side of the format for collections
+    that were added from device tensors or synthetic generators."""
+    os.makedirs(out_dir, exist_ok=True)
+    paths = []
+    for s in range(index.num_shards):
+        p = os.path.join(out_dir, FLAT_NAME % s)
+        index.write_flat_file(p, shard=s)
+        paths.append(p)
+    return paths
+
+
 def flat_shard_rows(path: str) -> int:
     """Row count from a flat shard's header."""
     with open(path, "rb") as f:

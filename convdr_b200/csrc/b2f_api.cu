@@ -1894,6 +1894,74 @@ extern "C" int b2f_add_flat_file(b2f_index* idx, int shard, const char* path, in
   return B2F_OK;
 }
 
+// Writer side of the flat shard format (what `gen_passage_embeddings.py:146-169` +
+// `utils/util.py:105-111` do with pickles): dump the rows and labels of one device-resident shard to ONE flat
+// shard file that b2f_add_flat_file (or numpy.memmap, convdr_b200/blocks.py) reads back.  Rows leave the device
+// in 24 MB pieces through two pinned buffers, the copy of piece i+1 overlapping the write of piece i.
+extern "C" int b2f_write_flat_file(b2f_index* idx, int shard, const char* path) {
+  if (!idx || !path || shard < 0 || shard >= static_cast<int>(idx->shards.size()))
+    return fail(B2F_ERR_INVALID, "bad write_flat_file arguments");
+  B2F_TRY(settle_pending(idx));
+  Shard& S = idx->shards[shard];
+  CU_TRY(cudaSetDevice(S.dev));
+  CU_TRY(cudaStreamSynchronize(S.stream));
+  const int64_t n = S.n;
+  const size_t piece_bytes = static_cast<size_t>(kLoadPieceRows) * kD * 4;
+  for (int b = 0; b < 2; ++b) {
+    if ((!S.load_bufs[b] && cudaMallocHost(reinterpret_cast<void**>(&S.load_bufs[b]), piece_bytes) != cudaSuccess) ||
+        (!S.load_evs[b] && cudaEventCreateWithFlags(&S.load_evs[b], cudaEventDisableTiming) != cudaSuccess)) {
+      (void)cudaGetLastError();
+      return fail(B2F_ERR_OOM, "pinned staging allocation failed");
+    }
+  }
+  // labels: the explicit ones, or the implicit ids of the segments
+  std::vector<int64_t> ids(static_cast<size_t>(n));
+  if (n > 0) {
+    if (S.has_ids) {
+      CU_TRY(cudaMemcpy(ids.data(), S.idmap, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost));
+    } else {
+      for (const Seg& sg : S.segs)
+        for (int64_t i = 0; i < sg.count; ++i) ids[static_cast<size_t>(sg.local_start + i)] = sg.global_start + i;
+    }
+  }
+  FlatHeader h;
+  std::memcpy(h.magic, "B2FSHARD", 8);
+  h.version = 1; h.d = kD; h.n = static_cast<uint64_t>(n); h.dtype = 0;
+  h.rows_off = 64;
+  h.ids_off = static_cast<uint64_t>(round_up(static_cast<int64_t>(h.rows_off) + n * kD * 4, 64));
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE* f = std::fopen(tmp.c_str(), "wb");
+  if (!f) return fail(B2F_ERR_INVALID, "cannot create " + tmp);
+  auto bail = [&](int code, const std::string& msg) { std::fclose(f); std::remove(tmp.c_str()); return fail(code, msg); };
+  char head[64] = {0};
+  std::memcpy(head, &h, sizeof(h));
+  if (std::fwrite(head, 1, 64, f) != 64) return bail(B2F_ERR_INVALID, "write error on " + tmp);
+  const int64_t n_pieces = (n + kLoadPieceRows - 1) / kLoadPieceRows;
+  auto piece_rows = [&](int64_t i) { return std::min<int64_t>(kLoadPieceRows, n - i * kLoadPieceRows); };
+  for (int64_t i = 0; i <= n_pieces; ++i) {
+    if (i < n_pieces) {   // queue the copy of piece i
+      if (cudaMemcpyAsync(S.load_bufs[i & 1], S.x32 + i * kLoadPieceRows * kD, static_cast<size_t>(piece_rows(i)) * kD * 4,
+                          cudaMemcpyDeviceToHost, S.stream) != cudaSuccess ||
+          cudaEventRecord(S.load_evs[i & 1], S.stream) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return bail(B2F_ERR_CUDA, "device-to-host copy failed");
+      }
+    }
+    if (i >= 1) {         // ... while piece i-1 goes to the file
+      if (cudaEventSynchronize(S.load_evs[(i - 1) & 1]) != cudaSuccess) { (void)cudaGetLastError(); return bail(B2F_ERR_CUDA, "device-to-host copy failed"); }
+      const size_t bytes = static_cast<size_t>(piece_rows(i - 1)) * kD * 4;
+      if (std::fwrite(S.load_bufs[(i - 1) & 1], 1, bytes, f) != bytes) return bail(B2F_ERR_INVALID, "write error on " + tmp);
+    }
+  }
+  const size_t pad = static_cast<size_t>(h.ids_off - (h.rows_off + static_cast<uint64_t>(n) * kD * 4));
+  const char zeros[64] = {0};
+  if (pad && std::fwrite(zeros, 1, pad, f) != pad) return bail(B2F_ERR_INVALID, "write error on " + tmp);
+  if (n && std::fwrite(ids.data(), 8, static_cast<size_t>(n), f) != static_cast<size_t>(n)) return bail(B2F_ERR_INVALID, "write error on " + tmp);
+  if (std::fclose(f) != 0) { std::remove(tmp.c_str()); return fail(B2F_ERR_INVALID, "write error on " + tmp); }
+  if (std::rename(tmp.c_str(), path) != 0) { std::remove(tmp.c_str()); return fail(B2F_ERR_INVALID, std::string("cannot rename to ") + path); }
+  return B2F_OK;
+}
+
 extern "C" int b2f_rank_dedup_device(b2f_index* idx, const int64_t* I_dev, const float* D32_dev, const double* D64_dev,
                                      int64_t nq, int64_t in_stride, int topN, const int64_t* offset2pid_dev,
                                      int64_t n_offsets, int64_t* pid_out_dev, double* score_out_dev, int* count_out_dev) {

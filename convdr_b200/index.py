@@ -131,6 +131,12 @@ class FlatIPIndex:
                                                  C.byref(secs), C.byref(gb)))
         return float(secs.value), float(gb.value)
 
+    def write_flat_file(self, path: str, shard: int = 0) -> None:
+        """Dump one device-resident shard (rows + labels) to a flat shard file (b2f_write_flat_file) that
+        `add_flat_file` / `blocks.open_flat_shard` read back — the writer side of the block format for a
+        generator that hands its embeddings over on the device (`add_device`)."""
+        _lib.check(_lib.load().b2f_write_flat_file(self._ensure(), int(shard), str(path).encode()))
+
     def rank_dedup(self, I, D, topN: int, offset2pid):
         """EvalDevQuery's id handling on device (reference drivers/run_convdr_inference.py:43-69): I [nq, >=topN]
         int64 offsets (best first), D float32/float64 scores, offset2pid int64 [n] — all CUDA tensors on the

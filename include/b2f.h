@@ -84,6 +84,13 @@ int b2f_add_device(b2f_index* idx, int shard, const float* x_dev, int64_t n);
 int b2f_add_flat_file(b2f_index* idx, int shard, const char* path, int n_threads,
                       double* seconds_out, double* gbytes_out);
 
+/* Writer side of the same format (reference drivers/gen_passage_embeddings.py:146-169
+ * + utils/util.py:105-111 dump each rank's arrays as pickles): write the rows and
+ * labels of shard `shard` (explicit ids, or the implicit positions) to ONE flat shard
+ * file, straight from device memory through pinned staging buffers (the copy of a
+ * piece overlaps the write of the previous one); written to `path`.tmp, then renamed. */
+int b2f_write_flat_file(b2f_index* idx, int shard, const char* path);
+
 /* Pre-size every shard for `n_per_shard` rows (avoids regrowth copies).        */
 int b2f_reserve(b2f_index* idx, int64_t n_per_shard);
 

@@ -694,3 +694,35 @@ def test_merge_kernels_keep_the_tie_order_across_parts(n_parts):
     np.testing.assert_array_equal(Im.cpu().numpy(), Iw)
     np.testing.assert_array_equal(Dm.cpu().numpy(), Dw)
     assert (np.diff(Dw[0, :4 * n_parts]) == 0).sum() >= n_parts - 1      # the planted ties are really there
+
+
+def test_device_side_flat_shard_writer_round_trips(tmp_path):
+    """SURVEY §8 f4: b2f_write_flat_file dumps a device-resident shard (several staged pieces) to the flat format;
+    numpy's reader and the native loader both get the rows and labels back, explicit or implicit."""
+    from convdr_b200 import blocks
+    n = 20011
+    P = c_oracle.synth_block(0, n, seed=93)
+    ids = np.arange(n, dtype=np.int64) * 5 + 2
+    a = make_index("auto")
+    a.add_with_ids(P, ids)
+    paths = blocks.save_index_to_flat(a, str(tmp_path / "labelled"))
+    rows, got_ids = blocks.open_flat_shard(paths[0])
+    np.testing.assert_array_equal(np.asarray(rows), P)
+    np.testing.assert_array_equal(np.asarray(got_ids), ids)
+    b = make_index("auto")
+    assert blocks.load_flat_into(b, paths) == n
+    Q = c_oracle.synth_block(0, 17, seed=93, stream=1)
+    Da, Ia = a.search(Q, 40)
+    Db, Ib = b.search(Q, 40)
+    np.testing.assert_array_equal(Ia, Ib)
+    np.testing.assert_array_equal(Da, Db)
+    c = make_index("auto", P[:9000])             # implicit ids: the positions
+    c.add(P[9000:])
+    p2 = str(tmp_path / "implicit.b2f")
+    c.write_flat_file(p2)
+    _, ids2 = blocks.open_flat_shard(p2)
+    np.testing.assert_array_equal(np.asarray(ids2), np.arange(n))
+    e = make_index("auto")
+    p3 = str(tmp_path / "empty.b2f")
+    e.write_flat_file(p3)
+    assert blocks.flat_shard_rows(p3) == 0
