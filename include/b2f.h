@@ -225,6 +225,7 @@ void* b2f_stream(b2f_index* idx, int shard);
  *       2 TS = queries in TMEM, MMA M = 256 query lanes; 3 QS = queries on the MMA N side; 1 = QS with
  *       every query K-block resident in shared memory), "qs_resident_kb" (QS: resident query K-blocks,
  *       default 12; the rest is streamed from L2 through a ring of "qs_q_stages" stages),
+ *   "l2_prefetch" (QS: distance in tiles of an optional L2 prefetch warp; default 0 = off, measured slower),
  *   "synth_mean_shift" (b2f_add_synthetic: integer shift M of every component along a fixed sign
  *       vector per seed, 0 = isotropic rows; see convdr_b200/synth.py),
  *   "tighten" (TS engine: in-kernel threshold tightening, minimum pause of the refresher warp in
