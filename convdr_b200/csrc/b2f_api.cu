@@ -89,16 +89,17 @@ EncodeTiledFn get_encode_fn() {
 // bf16 tensor [rows, cols] with row pitch cols*2 bytes, box = 64 columns (128 bytes) x box_rows,
 // 128-byte swizzle.  Queries: cols = 768 (row-major).  Shadow: cols = 64 — the K-block-major tiled
 // layout (common.cuh) is a [tiles*12*128, 64] matrix of 128-byte rows.
-int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint32_t cols, uint32_t box_rows) {
+// `half_box`: boxes of 32 columns (64 bytes) with the 64-byte swizzle instead (the QS kernel's half stages).
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint32_t cols, uint32_t box_rows, bool half_box = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(B2F_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), rows};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(half_box ? kBlockK / 2 : kBlockK), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, half_box ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B2F_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
   return B2F_OK;
 }
@@ -299,6 +300,7 @@ struct b2f_index {
                           // (profiles/r02): fully resident wins for <= 208 queries — the re-read query bytes cost more
                           // L2->SM bandwidth and power than the deeper passage ring gains
   int qs_q_stages = 3;    // QS: depth of the query ring
+  int qs_half_stage = 0;  // QS: 1 = 8 KB half stages when only <= 5 full stages fit next to the resident queries
   int center = 1;         // subtract the collection mean (first rows of the first add) before the bf16 rounding
   int synth_mean_shift = 0;  // b2f_add_synthetic: integer shift of every component along a fixed sign vector
   int l2_prefetch = 0;    // QS: distance (tiles) of the optional L2 prefetch warp; 0 = off (default: measured slower)
@@ -686,15 +688,18 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
   if (tensor_qs) {
     // ---- QS: one launch over the whole shard, then the fused last step ----
     const int n_cols = static_cast<int>(round_up(nqp, 16));
-    const QsPlan qp = umma_qs_plan(n_cols, idx->umma_variant == 1 ? kNumKBlocks : idx->qs_resident_kb, idx->qs_q_stages);
-    CUtensorMap tmap_p, tmap_q;
+    const QsPlan qp = umma_qs_plan(n_cols, idx->umma_variant == 1 ? kNumKBlocks : idx->qs_resident_kb, idx->qs_q_stages,
+                                   idx->qs_half_stage);
+    CUtensorMap tmap_p, tmap_ph, tmap_q;
     const uint64_t srows = static_cast<uint64_t>(shadow_rows_padded(N)) * kNumKBlocks;
     B2F_TRY(make_tmap_bf16(&tmap_p, S.x16, srows, kBlockK, kShadowTileRows));        // one K-block of a 32-row tile
+    B2F_TRY(make_tmap_bf16(&tmap_ph, S.x16, srows, kBlockK, kShadowTileRows, true)); // half a K-block of a 32-row tile
     B2F_TRY(make_tmap_bf16(&tmap_q, q16p, static_cast<uint64_t>(n_cols), kD, static_cast<uint32_t>(n_cols / 2)));
     const int te = static_cast<int>((N + kQsTileRows - 1) / kQsTileRows);
     UmmaQsArgs a;
     a.n_rows = N; a.tile_begin = 0; a.tile_end = te; a.n_cols = n_cols; a.nq = nqp;
     a.a_stages = qp.a_stages; a.q_stages = qp.q_stages; a.resident_kb = qp.resident_kb; a.q16 = q16p;
+    a.half_stage = qp.half_stage;
     a.cand = W.cand[0]; a.C = C; a.S = plan.S; a.cap_p = plan.cap_a; a.n_areas = n_areas; a.cnt2 = W.cnt2;
     a.tau = W.tau; a.ovf = W.ovf; a.err = W.err; a.tighten = idx->tighten; a.tighten_adaptive = idx->tighten_adaptive;
     a.k = k; a.margin = W.margin; a.hist = W.hist; a.hkey0 = W.hkey0; a.hshift = W.hshift;
@@ -710,7 +715,7 @@ int enqueue_pass(b2f_index* idx, Shard& S, const PassPlan& plan, const float* q3
     a.first_wait_cycles = (idx->tighten && N >= 4ll * pairs * kQsTileRows && a.dense_quarters < 4) ? 100000 : 0;
     {
       ProfScope ps(idx, S, 0);
-      umma_qs_score_select_kernel<<<2 * pairs, kQsThreads, qp.smem_bytes, s>>>(tmap_p, tmap_q, a);
+      umma_qs_score_select_kernel<<<2 * pairs, kQsThreads, qp.smem_bytes, s>>>(tmap_p, tmap_ph, tmap_q, a);
     }
     CU_TRY(cudaGetLastError());
     st.score_rows += static_cast<double>(N);
@@ -1657,6 +1662,8 @@ int b2f_set_option(b2f_index* idx, const char* key, int64_t value) {
   } else if (k == "qs_q_stages") {
     if (value < 2 || value > kQsMaxQStages) return fail(B2F_ERR_INVALID, "qs_q_stages must be in [2, 4]");
     idx->qs_q_stages = static_cast<int>(value);
+  } else if (k == "qs_half_stage") {
+    idx->qs_half_stage = value ? 1 : 0;
   } else if (k == "center") {
     if (idx->ntotal > 0) return fail(B2F_ERR_INVALID, "center can only be changed on an empty index");
     idx->center = value ? 1 : 0;

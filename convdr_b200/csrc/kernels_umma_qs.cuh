@@ -69,14 +69,18 @@ struct UmmaQsArgs {
   const unsigned char* x16_bytes;   // base of the shadow (for the L2 prefetch)
   int64_t pf_limit_bytes;     // prefetches stay below this offset (end of the padded shadow rows)
   int prefetch;               // D > 0: warp 3 keeps an L2 prefetch (LSU path) D tiles ahead of the producer; 0: off
+  int half_stage;             // 1: ring stages are 8 KB half K-blocks (64B swizzle), 2 MMAs per stage; 0: 16 KB, 4 MMAs
   int dense_quarters;         // first tile of a CTA: lane quarters [0, dense_quarters) pass unfiltered
   int first_wait_cycles;      // the other quarters wait this long at most for every threshold to exist (0: no wait)
 };
 
-struct QsPlan { int a_stages, q_stages, resident_kb, smem_bytes; };
+struct QsPlan { int a_stages, q_stages, resident_kb, smem_bytes, half_stage; };
 
 // Shared-memory budget: [resident query K-blocks][query ring][passage ring][tail].
-inline QsPlan umma_qs_plan(int n_cols, int resident_kb, int q_stages) {
+// half_stage_mode: 0 never, 1 = use 8 KB half stages (128 rows x 32 K-elements, 64B swizzle) when the queries are
+// fully resident and only <= 5 full 16 KB stages fit (161..176+ queries): 11 half stages keep 88 KB in flight
+// instead of 80 KB and recycle ring slots at twice the granularity.
+inline QsPlan umma_qs_plan(int n_cols, int resident_kb, int q_stages, int half_stage_mode = 0) {
   const int qkb = (n_cols / 2) * 128;
   if (resident_kb < 0) resident_kb = 0;
   if (resident_kb > kNumKBlocks) resident_kb = kNumKBlocks;
@@ -89,12 +93,25 @@ inline QsPlan umma_qs_plan(int n_cols, int resident_kb, int q_stages) {
     int a = avail / kQsStageBytes;
     if (a > kQsMaxAStages) a = kQsMaxAStages;
     if (a >= 4 || resident_kb == 0) {
-      p.a_stages = a; p.q_stages = qs; p.resident_kb = resident_kb;
-      p.smem_bytes = (resident_kb + qs) * qkb + a * kQsStageBytes + kQsTailBytes + 1024;
+      p.a_stages = a; p.q_stages = qs; p.resident_kb = resident_kb; p.half_stage = 0;
+      if (half_stage_mode && resident_kb == kNumKBlocks && a <= 5) {
+        int ah = avail / (kQsStageBytes / 2);
+        if (ah > kQsMaxAStages) ah = kQsMaxAStages;
+        if (ah * (kQsStageBytes / 2) > a * kQsStageBytes) { p.half_stage = 1; p.a_stages = ah; }
+      }
+      p.smem_bytes = (resident_kb + qs) * qkb + (p.half_stage ? p.a_stages * (kQsStageBytes / 2) : a * kQsStageBytes) +
+                     kQsTailBytes + 1024;
       return p;
     }
     --resident_kb;   // too many resident K-blocks for this batch size: stream more of them
   }
+}
+
+// K-major, 64-byte-swizzled operand descriptor: rows of 64 bytes (32 bf16), 8-row groups 512 bytes apart,
+// swizzle mode 4 (64B) in bits [61,64) — the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_64B.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu) | (static_cast<uint64_t>(512 >> 4) << 32) |
+         (1ull << 46) | (4ull << 61);
 }
 
 __device__ __forceinline__ float4 lds_volatile_f4(uint32_t addr) {
@@ -151,6 +168,7 @@ __device__ __forceinline__ bool any_ge16(const uint32_t (&v)[16], const float (&
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
     umma_qs_score_select_kernel(const __grid_constant__ CUtensorMap tmap_p,
+                                const __grid_constant__ CUtensorMap tmap_ph /* 32-column boxes, 64B swizzle */,
                                 const __grid_constant__ CUtensorMap tmap_q, const UmmaQsArgs a) {
   extern __shared__ unsigned char umma_smem_raw[];
   const uint32_t raw = smem_u32(umma_smem_raw);
@@ -163,7 +181,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
   const uint32_t smem_qres = base;
   const uint32_t smem_qring = base + static_cast<uint32_t>(R) * qkb_bytes;
   const uint32_t smem_a = smem_qring + static_cast<uint32_t>(a.q_stages) * qkb_bytes;
-  const uint32_t tail_off = static_cast<uint32_t>(R + a.q_stages) * qkb_bytes + static_cast<uint32_t>(a.a_stages) * kQsStageBytes;
+  const uint32_t a_stage_bytes = a.half_stage ? kQsStageBytes / 2 : kQsStageBytes;
+  const int n_sub = a.half_stage ? 2 : 1;          // ring stages per K-block
+  const uint32_t tail_off = static_cast<uint32_t>(R + a.q_stages) * qkb_bytes + static_cast<uint32_t>(a.a_stages) * a_stage_bytes;
   const uint32_t tail = base + tail_off;
   const uint32_t bar_afull = tail;                               // [kQsMaxAStages]
   const uint32_t bar_aempty = tail + 8 * kQsMaxAStages;          // [kQsMaxAStages]
@@ -190,6 +210,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_p);
+    prefetch_tmap(&tmap_ph);
     prefetch_tmap(&tmap_q);
   }
   if (warp == 1 && lane == 0) {
@@ -235,15 +256,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
       // each is a contiguous 4 KB piece -> 4 TMA boxes per 16 KB stage (rows past the end: zero fill)
       const int t32 = (tile * 2 + static_cast<int>(cta_rank)) * (kQsTileRowsCta / kShadowTileRows);
       for (int kb = 0; kb < kNumKBlocks; ++kb) {
-        mbar_wait(bar_aempty + 8 * stage, phase ^ 1u, a.err);
-        const uint32_t full_leader = mapa_u32(bar_afull + 8 * stage, 0);
-        if (leader) mbar_arrive_expect_tx(bar_afull + 8 * stage, 2u * kQsStageBytes);
-        else mbar_arrive_cluster(full_leader);
+        for (int h = 0; h < n_sub; ++h) {
+          mbar_wait(bar_aempty + 8 * stage, phase ^ 1u, a.err);
+          const uint32_t full_leader = mapa_u32(bar_afull + 8 * stage, 0);
+          if (leader) mbar_arrive_expect_tx(bar_afull + 8 * stage, 2u * a_stage_bytes);
+          else mbar_arrive_cluster(full_leader);
+          if (a.half_stage) {
 #pragma unroll
-        for (int j = 0; j < kQsTileRowsCta / kShadowTileRows; ++j)
-          tma_load_2d_2sm(smem_a + stage * kQsStageBytes + j * (kShadowTileRows * 128), &tmap_p, full_leader, 0,
-                          ((t32 + j) * kNumKBlocks + kb) * kShadowTileRows, kHintEvictFirst);
-        if (++stage == static_cast<uint32_t>(a.a_stages)) { stage = 0; phase ^= 1u; }
+            for (int j = 0; j < kQsTileRowsCta / kShadowTileRows; ++j)
+              tma_load_2d_2sm(smem_a + stage * a_stage_bytes + j * (kShadowTileRows * 64), &tmap_ph, full_leader, 32 * h,
+                              ((t32 + j) * kNumKBlocks + kb) * kShadowTileRows, kHintEvictFirst);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kQsTileRowsCta / kShadowTileRows; ++j)
+              tma_load_2d_2sm(smem_a + stage * a_stage_bytes + j * (kShadowTileRows * 128), &tmap_p, full_leader, 0,
+                              ((t32 + j) * kNumKBlocks + kb) * kShadowTileRows, kHintEvictFirst);
+          }
+          if (++stage == static_cast<uint32_t>(a.a_stages)) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 2 && lane == 0) {
@@ -306,21 +336,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQsThreads, 1)
       const uint32_t tmem_d = tmem_base + as * kQsAccStride;
       for (int kb = 0; kb < kNumKBlocks; ++kb) {
         const bool streamed = kb >= R;
-        mbar_wait(bar_afull + 8 * sa, pa, a.err);
         if (streamed) mbar_wait(bar_qfull + 8 * sq, pq, a.err);
-        tc_fence_after();
-        if (elected) {
-          const uint64_t adesc = umma_desc_sw128(smem_a + sa * kQsStageBytes);
-          const uint64_t bdesc = umma_desc_sw128(streamed ? smem_qring + sq * qkb_bytes : smem_qres + kb * qkb_bytes);
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)  // UMMA K = 16 bf16 = 32 bytes = 2 descriptor units
-            umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_pair(bar_aempty + 8 * sa);                 // frees the passage stage in both CTAs
-          if (streamed) umma_commit_pair(bar_qempty + 8 * sq);   // and the query stage
-          if (kb == kNumKBlocks - 1) umma_commit_pair(bar_tfull + 8 * as);  // accumulator ready
+        for (int h = 0; h < n_sub; ++h) {
+          mbar_wait(bar_afull + 8 * sa, pa, a.err);
+          tc_fence_after();
+          if (elected) {
+            const uint32_t a_addr = smem_a + sa * a_stage_bytes;
+            const uint64_t adesc = a.half_stage ? umma_desc_sw64(a_addr) : umma_desc_sw128(a_addr);
+            const uint64_t bdesc = umma_desc_sw128(streamed ? smem_qring + sq * qkb_bytes : smem_qres + kb * qkb_bytes);
+            const int k_steps = a.half_stage ? 2 : 4;     // UMMA K = 16 bf16 = 32 bytes = 2 descriptor units
+            for (int k = 0; k < k_steps; ++k) {
+              const int kq = a.half_stage ? 2 * h + k : k;   // position of this K-step inside the query K-block
+              umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * kq, idesc, (kb | h | k) != 0);
+            }
+            umma_commit_pair(bar_aempty + 8 * sa);                 // frees the passage stage in both CTAs
+            if (h == n_sub - 1) {
+              if (streamed) umma_commit_pair(bar_qempty + 8 * sq);   // and the query stage
+              if (kb == kNumKBlocks - 1) umma_commit_pair(bar_tfull + 8 * as);  // accumulator ready
+            }
+          }
+          __syncwarp();
+          if (++sa == static_cast<uint32_t>(a.a_stages)) { sa = 0; pa ^= 1u; }
         }
-        __syncwarp();
-        if (++sa == static_cast<uint32_t>(a.a_stages)) { sa = 0; pa ^= 1u; }
         if (streamed && ++sq == static_cast<uint32_t>(a.q_stages)) { sq = 0; pq ^= 1u; }
       }
     }

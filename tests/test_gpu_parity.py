@@ -19,8 +19,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # umma_*: the tensor-engine variants — qs (queries streamed on the MMA N side, the default up to 208 queries per
 # pass), qsr (same kernel, every query K-block resident in shared memory), ts (queries in TMEM)
-PATHS = ["scan_f32", "scan_exact", "umma_qs", "umma_qsr", "umma_ts"]
-UMMA_VARIANT = {"umma_qsr": 1, "umma_ts": 2, "umma_qs": 3}
+# qsh: QS with 8 KB half stages (64B swizzle) wherever <= 5 full stages would fit (161+ queries per pass)
+PATHS = ["scan_f32", "scan_exact", "umma_qs", "umma_qsr", "umma_qsh", "umma_ts"]
+UMMA_VARIANT = {"umma_qsr": 1, "umma_ts": 2, "umma_qs": 3, "umma_qsh": 3}
 RTOL = 1e-5          # the tolerance north_star states
 RTOL_TRUTH = 1e-6    # what the exact rescoring actually delivers vs float64
 
@@ -29,6 +30,7 @@ def make_index(path, P=None, devices=None, **opts):
     idx = FlatIPIndex(768, devices=devices)
     if path in UMMA_VARIANT:
         idx.set_option("umma_variant", UMMA_VARIANT[path])
+        idx.set_option("qs_half_stage", 1 if path == "umma_qsh" else 0)
         path = "umma_bf16"
     idx.set_option("path", path)
     for k, v in opts.items():
