@@ -226,6 +226,7 @@ void* b2f_stream(b2f_index* idx, int shard);
  *       every query K-block resident in shared memory), "qs_resident_kb" (QS: resident query K-blocks,
  *       default 12; the rest is streamed from L2 through a ring of "qs_q_stages" stages),
  *   "l2_prefetch" (QS: distance in tiles of an optional L2 prefetch warp; default 0 = off, measured slower),
+ *   "qs_half_stage" (QS: 8 KB half stages with the 64-byte swizzle when <= 5 full stages fit; default 0, measured slower),
  *   "synth_mean_shift" (b2f_add_synthetic: integer shift M of every component along a fixed sign
  *       vector per seed, 0 = isotropic rows; see convdr_b200/synth.py),
  *   "tighten" (TS engine: in-kernel threshold tightening, minimum pause of the refresher warp in
